@@ -1,0 +1,108 @@
+"""ctypes binding of ``libi2v_attn_b200.so`` (C ABI declared in ``include/i2v_attn_b200.h``).
+
+This module is deliberately thin: it loads the in-tree shared library, declares the argument types of every exported
+symbol and turns negative status codes into Python exceptions.  There is no fallback of any kind: if the library is
+missing, cannot be loaded, or the device is not sm_100, the error propagates to the caller.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libi2v_attn_b200.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+
+I2V_BF16, I2V_F32 = 0, 1
+MODE_AUTO, MODE_FAST, MODE_GENERIC = 0, 1, 2
+
+#: every symbol include/i2v_attn_b200.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTED_SYMBOLS = (
+    "i2v_version",
+    "i2v_last_error",
+    "i2v_device_supported",
+    "i2v_launch_count",
+    "i2v_sdpa_fwd",
+    "i2v_fused_self_xframe_fwd",
+    "i2v_ip_xattn_fwd",
+    "i2v_temporal_attn_fwd",
+    "i2v_reshard_pack",
+    "i2v_reshard_unpack",
+    "i2v_set_tuning",
+)
+
+
+class I2VTensor(ctypes.Structure):
+    """Mirror of ``i2v_tensor``: device pointer + element strides (batch, seq, head); d is contiguous."""
+
+    _fields_ = [
+        ("data", ctypes.c_void_p),
+        ("stride_b", ctypes.c_int64),
+        ("stride_s", ctypes.c_int64),
+        ("stride_h", ctypes.c_int64),
+    ]
+
+
+class I2VLibraryError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libi2v_attn_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    T = ctypes.POINTER(I2VTensor)
+    i, f, p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+    lib.i2v_version.restype = i
+    lib.i2v_version.argtypes = []
+    lib.i2v_last_error.restype = ctypes.c_char_p
+    lib.i2v_last_error.argtypes = []
+    lib.i2v_device_supported.restype = i
+    lib.i2v_device_supported.argtypes = []
+    lib.i2v_launch_count.restype = ctypes.c_int64
+    lib.i2v_launch_count.argtypes = []
+    lib.i2v_sdpa_fwd.restype = i
+    lib.i2v_sdpa_fwd.argtypes = [T, T, T, T, i, i, i, i, i, i, f, i, i, p]
+    lib.i2v_fused_self_xframe_fwd.restype = i
+    lib.i2v_fused_self_xframe_fwd.argtypes = [T, T, T, T, T, T, T, T, i, i, i, i, i, f, i, i, p]
+    lib.i2v_ip_xattn_fwd.restype = i
+    lib.i2v_ip_xattn_fwd.argtypes = [T, T, T, T, T, T, i, i, i, i, i, i, i, f, f, i, i, p]
+    lib.i2v_temporal_attn_fwd.restype = i
+    lib.i2v_temporal_attn_fwd.argtypes = [T, T, T, T, i, i, i, i, f, i, i, p]
+    lib.i2v_reshard_pack.restype = i
+    lib.i2v_reshard_pack.argtypes = [p, p, i, i, i, i, i, i, i, p]
+    lib.i2v_reshard_unpack.restype = i
+    lib.i2v_reshard_unpack.argtypes = [p, p, i, i, i, i, i, i, i, p]
+    lib.i2v_set_tuning.restype = i
+    lib.i2v_set_tuning.argtypes = [i, i]
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises ``FileNotFoundError`` / ``OSError`` when it is absent or broken."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU or PyTorch fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        msg = load().i2v_last_error()
+        raise I2VLibraryError(code, msg.decode("utf-8", "replace") if msg else "")
+
+
+def launch_count() -> int:
+    return int(load().i2v_launch_count())

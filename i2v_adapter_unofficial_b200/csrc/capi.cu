@@ -1,0 +1,493 @@
+// C-ABI entry points of libi2v_attn_b200.so (declared in include/i2v_attn_b200.h): argument validation,
+// TMA tensor-map encoding, kernel selection and launch.  No torch types, no CPU compute path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/i2v_attn_b200.h"
+#include "dense_attn_sm100.cuh"
+#include "generic_attn.cuh"
+#include "temporal_attn.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) return fail(I2V_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceInfo {
+  int ok = -1;  // -1 unknown
+  int sms = 0;
+  int major = 0, minor = 0;
+};
+DeviceInfo g_dev[64];
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(I2V_ERR_NO_DEVICE, "cudaGetDevice: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return fail(I2V_ERR_NO_DEVICE, "device ordinal %d out of range", dev);
+  DeviceInfo& d = g_dev[dev];
+  if (d.ok < 0) {
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return fail(I2V_ERR_NO_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    d.sms = p.multiProcessorCount;
+    d.major = p.major;
+    d.minor = p.minor;
+    d.ok = (p.major == 10) ? 1 : 0;
+  }
+  if (!d.ok)
+    return fail(I2V_ERR_NO_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", dev, d.major,
+                d.minor);
+  *out = &d;
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode_fn() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr)
+    return fail(I2V_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (%s)", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_tensor(const char* name, const i2v_tensor* t, int elem_bytes, bool need_vec) {
+  if (t == nullptr || t->data == nullptr) return fail(I2V_ERR_BAD_SHAPE, "%s: null tensor", name);
+  if (need_vec) {
+    const int vec = 16 / elem_bytes;
+    if (!aligned16(t->data)) return fail(I2V_ERR_MISALIGNED, "%s: data pointer is not 16-byte aligned", name);
+    if (t->stride_b % vec || t->stride_s % vec || t->stride_h % vec)
+      return fail(I2V_ERR_MISALIGNED, "%s: strides must be multiples of %d elements", name, vec);
+  }
+  return 0;
+}
+
+// 4-D bf16 tensor map over a logical [batch, seq, heads, d] tensor: dims (d, heads, seq, batch),
+// box (64, 1, box_rows, 1), 128-byte swizzle, out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap* tm, const i2v_tensor* t, int batch, int seq, int heads, int d, int box_rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)seq, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)t->stride_h * 2, (cuuint64_t)t->stride_s * 2, (cuuint64_t)t->stride_b * 2};
+  // a size-1 dimension may carry any stride; keep the encoder happy with a 16-byte multiple
+  if (heads == 1 && strides[0] == 0) strides[0] = (cuuint64_t)d * 2;
+  if (batch == 1 && strides[2] == 0) strides[2] = (cuuint64_t)t->stride_s * 2 * seq;
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->data, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(I2V_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (CUresult %d) dims=(%d,%d,%d,%d) strides(B)=(%lld,%lld,%lld)", (int)r, d,
+                heads, seq, batch, (long long)strides[0], (long long)strides[1], (long long)strides[2]);
+  return 0;
+}
+
+struct DenseSeg {
+  const i2v_tensor *q, *k, *v, *o;
+  int kv_group;
+};
+
+int dense_dk(int d) {
+  const int dk = (d + 15) / 16 * 16;
+  switch (dk) {
+    case 16: case 32: case 48: case 64: case 80: case 96: case 128: case 160: return dk;
+    default: return 0;
+  }
+}
+int dense_block_n(int dk) { return dk > 128 ? 64 : 128; }
+
+bool dense_supported(int d, int dtype) { return dtype == I2V_BF16 && d % 8 == 0 && dense_dk(d) != 0; }
+
+template <class Cfg>
+int launch_dense_cfg(const i2v::DenseParams& P, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = i2v::dense_attn_kernel<Cfg>;
+  if (!attr_set[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev & 63] = true;
+  }
+  const long long grid = (long long)P.q_blocks * P.heads * P.batch * P.nprob;
+  if (grid <= 0 || grid > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "dense attention grid %lld out of range", grid);
+  kern<<<(unsigned)grid, i2v::kDenseThreads, Cfg::SMEM_BYTES, stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, int skv, int d, float scale,
+                 int seg_split, float seg_scale, cudaStream_t stream) {
+  int rc = get_encode_fn();
+  if (rc) return rc;
+  const int dk = dense_dk(d);
+  const int bn = dense_block_n(dk);
+  if (seg_split >= 0 && skv > bn)
+    return fail(I2V_ERR_UNSUPPORTED, "two-segment softmax needs skv (%d) <= %d", skv, bn);
+  i2v::DenseParams P;
+  memset(&P, 0, sizeof(P));
+  P.nprob = nseg;
+  P.batch = batch; P.heads = heads; P.sq = sq; P.skv = skv; P.d = d;
+  P.q_blocks = (sq + 255) / 256;
+  P.scale_log2e = scale * 1.4426950408889634f;
+  P.seg_split = seg_split;
+  P.seg_scale = seg_scale;
+  for (int i = 0; i < nseg; ++i) {
+    const DenseSeg& s = segs[i];
+    if (batch % s.kv_group) return fail(I2V_ERR_BAD_SHAPE, "batch %d not divisible by kv_group %d", batch, s.kv_group);
+    if ((rc = check_tensor("q", s.q, 2, true)) || (rc = check_tensor("k", s.k, 2, true)) ||
+        (rc = check_tensor("v", s.v, 2, true)) || (rc = check_tensor("o", s.o, 2, true)))
+      return rc;
+    if ((rc = make_tmap(&P.prob[i].tm_q, s.q, batch, sq, heads, d, 128))) return rc;
+    if ((rc = make_tmap(&P.prob[i].tm_k, s.k, batch / s.kv_group, skv, heads, d, bn))) return rc;
+    if ((rc = make_tmap(&P.prob[i].tm_v, s.v, batch / s.kv_group, skv, heads, d, bn))) return rc;
+    P.prob[i].o = reinterpret_cast<__nv_bfloat16*>(s.o->data);
+    P.prob[i].o_sb = s.o->stride_b; P.prob[i].o_ss = s.o->stride_s; P.prob[i].o_sh = s.o->stride_h;
+    P.prob[i].kv_group = s.kv_group;
+  }
+  switch (dk) {
+    case 16:  return launch_dense_cfg<i2v::DenseCfg<16, 128, 4>>(P, stream);
+    case 32:  return launch_dense_cfg<i2v::DenseCfg<32, 128, 4>>(P, stream);
+    case 48:  return launch_dense_cfg<i2v::DenseCfg<48, 128, 4>>(P, stream);
+    case 64:  return launch_dense_cfg<i2v::DenseCfg<64, 128, 4>>(P, stream);
+    case 80:  return launch_dense_cfg<i2v::DenseCfg<80, 128, 2>>(P, stream);
+    case 96:  return launch_dense_cfg<i2v::DenseCfg<96, 128, 2>>(P, stream);
+    case 128: return launch_dense_cfg<i2v::DenseCfg<128, 128, 2>>(P, stream);
+    case 160: return launch_dense_cfg<i2v::DenseCfg<160, 64, 2>>(P, stream);
+  }
+  return fail(I2V_ERR_UNSUPPORTED, "head dim %d not covered by the tcgen05 kernels", d);
+}
+
+int launch_generic(const i2v_tensor* q, const i2v_tensor* k, const i2v_tensor* v, const i2v_tensor* o,
+                   const i2v_tensor* k2, const i2v_tensor* v2, int batch, int heads, int sq, int skv, int skv2, int d,
+                   int kv_group, float scale, float scale2, int dtype, cudaStream_t stream) {
+  if (d > 160) return fail(I2V_ERR_UNSUPPORTED, "generic kernel supports head dim <= 160 (got %d)", d);
+  const int eb = dtype == I2V_F32 ? 4 : 2;
+  int rc;
+  if ((rc = check_tensor("q", q, eb, false)) || (rc = check_tensor("k", k, eb, false)) ||
+      (rc = check_tensor("v", v, eb, false)) || (rc = check_tensor("o", o, eb, false)))
+    return rc;
+  i2v::GenericParams P;
+  memset(&P, 0, sizeof(P));
+  P.q = q->data; P.k = k->data; P.v = v->data; P.o = o->data;
+  P.q_sb = q->stride_b; P.q_ss = q->stride_s; P.q_sh = q->stride_h;
+  P.k_sb = k->stride_b; P.k_ss = k->stride_s; P.k_sh = k->stride_h;
+  P.v_sb = v->stride_b; P.v_ss = v->stride_s; P.v_sh = v->stride_h;
+  P.o_sb = o->stride_b; P.o_ss = o->stride_s; P.o_sh = o->stride_h;
+  P.batch = batch; P.heads = heads; P.sq = sq; P.skv = skv; P.d = d; P.kv_group = kv_group; P.scale = scale;
+  if (skv2 > 0) {
+    if ((rc = check_tensor("k_ip", k2, eb, false)) || (rc = check_tensor("v_ip", v2, eb, false))) return rc;
+    P.k2 = k2->data; P.v2 = v2->data;
+    P.k2_sb = k2->stride_b; P.k2_ss = k2->stride_s; P.k2_sh = k2->stride_h;
+    P.v2_sb = v2->stride_b; P.v2_ss = v2->stride_s; P.v2_sh = v2->stride_h;
+    P.skv2 = skv2; P.scale2 = scale2;
+  }
+  const long long grid = (long long)((sq + i2v::kGenRows - 1) / i2v::kGenRows) * heads * batch;
+  if (grid <= 0 || grid > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "generic attention grid %lld out of range", grid);
+  const size_t smem = 2 * i2v::kGenKeys * (d + 1) * sizeof(float);
+  const int threads = i2v::kGenRows * i2v::kGenSlices;
+  const bool small = d <= 64;
+  if (dtype == I2V_F32) {
+    if (small) i2v::generic_attn_kernel<float, 16><<<(unsigned)grid, threads, smem, stream>>>(P);
+    else       i2v::generic_attn_kernel<float, 40><<<(unsigned)grid, threads, smem, stream>>>(P);
+  } else {
+    if (small) i2v::generic_attn_kernel<__nv_bfloat16, 16><<<(unsigned)grid, threads, smem, stream>>>(P);
+    else       i2v::generic_attn_kernel<__nv_bfloat16, 40><<<(unsigned)grid, threads, smem, stream>>>(P);
+  }
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int check_common(int batch, int heads, int sq, int skv, int d, int dtype, int mode) {
+  if (batch <= 0 || heads <= 0 || sq <= 0 || skv <= 0 || d <= 0)
+    return fail(I2V_ERR_BAD_SHAPE, "sizes must be positive (batch=%d heads=%d sq=%d skv=%d d=%d)", batch, heads, sq, skv,
+                d);
+  if (dtype != I2V_BF16 && dtype != I2V_F32) return fail(I2V_ERR_BAD_DTYPE, "dtype %d is not I2V_BF16 / I2V_F32", dtype);
+  if (mode < I2V_MODE_AUTO || mode > I2V_MODE_GENERIC) return fail(I2V_ERR_BAD_SHAPE, "unknown mode %d", mode);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// temporal
+// ---------------------------------------------------------------------------------------------------------
+template <int D, int HG, int FT>
+int launch_temporal_cfg(const i2v::TemporalParams& P, int sms, cudaStream_t stream) {
+  using Cfg = i2v::TemporalCfg<D, HG, FT>;
+  int stages = g_tuning[0] > 0 ? g_tuning[0] : 4;
+  const int budget = 200 * 1024;
+  while (stages > 2 && stages * Cfg::STAGE_BYTES + 256 > budget) --stages;
+  if (stages > 8) stages = 8;
+  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + 256 + 128;
+  if (smem > 227 * 1024) return fail(I2V_ERR_UNSUPPORTED, "temporal stage (%d B) does not fit shared memory", Cfg::STAGE_BYTES);
+  auto kern = i2v::temporal_attn_kernel<D, HG, FT>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long units = (long long)P.n_pos * (P.heads / HG);
+  const int per_sm = g_tuning[1] > 0 ? g_tuning[1] : 1;
+  long long grid = (long long)sms * per_sm;
+  if (grid > units) grid = units;
+  kern<<<(unsigned)grid, i2v::kTemporalThreads, smem, stream>>>(P, stages);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+template <int D, int HG>
+int launch_temporal_ft(const i2v::TemporalParams& P, int sms, cudaStream_t stream) {
+  if (P.frames <= 16) return launch_temporal_cfg<D, HG, 1>(P, sms, stream);
+  return launch_temporal_cfg<D, HG, 2>(P, sms, stream);
+}
+
+bool temporal_supported(int heads, int frames, int d, int dtype, const i2v_tensor* q, const i2v_tensor* k,
+                        const i2v_tensor* v, const i2v_tensor* o) {
+  if (dtype != I2V_BF16 || frames > 32) return false;
+  if (!(d == 16 || d == 32 || d == 40 || d == 64 || d == 80 || d == 128 || d == 160)) return false;
+  const int hg = d <= 80 ? 8 : 4;
+  if (heads % hg) return false;
+  if (q->stride_h != d || k->stride_h != d || v->stride_h != d || o->stride_h != d) return false;
+  return true;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int i2v_version(void) { return 100; }
+const char* i2v_last_error(void) { return g_err; }
+int64_t i2v_launch_count(void) { return g_launches.load(); }
+
+int i2v_device_supported(void) {
+  DeviceInfo* di = nullptr;
+  return device_info(&di) == 0 ? 1 : 0;
+}
+
+int i2v_set_tuning(int key, int value) {
+  if (key < 0 || key >= 8) return fail(I2V_ERR_BAD_SHAPE, "unknown tuning key %d", key);
+  g_tuning[key] = value;
+  return 0;
+}
+
+int i2v_sdpa_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_tensor* v, const i2v_tensor* o, int batch,
+                 int heads, int sq, int skv, int d, int kv_group, float scale, int dtype, int mode, void* stream) {
+  int rc = check_common(batch, heads, sq, skv, d, dtype, mode);
+  if (rc) return rc;
+  if (kv_group <= 0 || batch % kv_group) return fail(I2V_ERR_BAD_SHAPE, "batch %d not divisible by kv_group %d", batch, kv_group);
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  const bool fast_ok = dense_supported(d, dtype);
+  if (mode == I2V_MODE_FAST && !fast_ok)
+    return fail(I2V_ERR_UNSUPPORTED, "i2v_sdpa_fwd: FAST path needs bf16 and a supported head dim (d=%d dtype=%d)", d, dtype);
+  if (mode != I2V_MODE_GENERIC && fast_ok) {
+    DenseSeg seg{q, k, v, o, kv_group};
+    return launch_dense(&seg, 1, batch, heads, sq, skv, d, scale, -1, 0.f, (cudaStream_t)stream);
+  }
+  return launch_generic(q, k, v, o, nullptr, nullptr, batch, heads, sq, skv, 0, d, kv_group, scale, 0.f, dtype,
+                        (cudaStream_t)stream);
+}
+
+int i2v_fused_self_xframe_fwd(const i2v_tensor* q_self, const i2v_tensor* k_self, const i2v_tensor* v_self,
+                              const i2v_tensor* o_self, const i2v_tensor* q_x, const i2v_tensor* k_x,
+                              const i2v_tensor* v_x, const i2v_tensor* o_x, int batch, int heads, int seq, int d,
+                              int num_frames, float scale, int dtype, int mode, void* stream) {
+  int rc = check_common(batch, heads, seq, seq, d, dtype, mode);
+  if (rc) return rc;
+  // same checks (and messages) as the reference block: src/modules/i2v_adapter.py:477-481
+  if (num_frames <= 0) return fail(I2V_ERR_BAD_SHAPE, "`num_frames` must be provided when `enable_cross_frame_attn` is True.");
+  if (batch % num_frames)
+    return fail(I2V_ERR_BAD_SHAPE, "Batch size %d must be divisible by the number of frames %d.", batch, num_frames);
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  const bool fast_ok = dense_supported(d, dtype);
+  if (mode == I2V_MODE_FAST && !fast_ok)
+    return fail(I2V_ERR_UNSUPPORTED, "i2v_fused_self_xframe_fwd: FAST path needs bf16 and a supported head dim (d=%d)", d);
+  if (mode != I2V_MODE_GENERIC && fast_ok) {
+    DenseSeg segs[2] = {{q_self, k_self, v_self, o_self, 1}, {q_x, k_x, v_x, o_x, num_frames}};
+    return launch_dense(segs, 2, batch, heads, seq, seq, d, scale, -1, 0.f, (cudaStream_t)stream);
+  }
+  rc = launch_generic(q_self, k_self, v_self, o_self, nullptr, nullptr, batch, heads, seq, seq, 0, d, 1, scale, 0.f,
+                      dtype, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_generic(q_x, k_x, v_x, o_x, nullptr, nullptr, batch, heads, seq, seq, 0, d, num_frames, scale, 0.f,
+                        dtype, (cudaStream_t)stream);
+}
+
+int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_tensor* v_txt, const i2v_tensor* k_ip,
+                     const i2v_tensor* v_ip, const i2v_tensor* o, int batch, int heads, int sq, int n_txt, int n_ip,
+                     int d, int kv_group, float scale, float ip_scale, int dtype, int mode, void* stream) {
+  int rc = check_common(batch, heads, sq, n_txt, d, dtype, mode);
+  if (rc) return rc;
+  if (n_ip <= 0) return fail(I2V_ERR_BAD_SHAPE, "n_ip must be positive (got %d)", n_ip);
+  if (kv_group <= 0 || batch % kv_group) return fail(I2V_ERR_BAD_SHAPE, "batch %d not divisible by kv_group %d", batch, kv_group);
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  if (!k_txt || !v_txt || !k_ip || !v_ip) return fail(I2V_ERR_BAD_SHAPE, "null key/value tensor");
+  const int eb = dtype == I2V_F32 ? 4 : 2;
+  const bool contiguous_tokens =
+      (const char*)k_ip->data == (const char*)k_txt->data + (long long)n_txt * k_txt->stride_s * eb &&
+      (const char*)v_ip->data == (const char*)v_txt->data + (long long)n_txt * v_txt->stride_s * eb &&
+      k_ip->stride_b == k_txt->stride_b && k_ip->stride_s == k_txt->stride_s && k_ip->stride_h == k_txt->stride_h &&
+      v_ip->stride_b == v_txt->stride_b && v_ip->stride_s == v_txt->stride_s && v_ip->stride_h == v_txt->stride_h;
+  const bool fast_ok =
+      dense_supported(d, dtype) && contiguous_tokens && (n_txt + n_ip) <= dense_block_n(dense_dk(d));
+  if (mode == I2V_MODE_FAST && !fast_ok)
+    return fail(I2V_ERR_UNSUPPORTED,
+                "i2v_ip_xattn_fwd: FAST path needs bf16, supported head dim, image tokens stored right after the text "
+                "tokens and n_txt+n_ip <= tile (d=%d n_txt=%d n_ip=%d contiguous=%d)", d, n_txt, n_ip, (int)contiguous_tokens);
+  if (mode != I2V_MODE_GENERIC && fast_ok) {
+    DenseSeg seg{q, k_txt, v_txt, o, kv_group};
+    return launch_dense(&seg, 1, batch, heads, sq, n_txt + n_ip, d, scale, n_txt, ip_scale, (cudaStream_t)stream);
+  }
+  return launch_generic(q, k_txt, v_txt, o, k_ip, v_ip, batch, heads, sq, n_txt, n_ip, d, kv_group, scale, ip_scale,
+                        dtype, (cudaStream_t)stream);
+}
+
+int i2v_temporal_attn_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_tensor* v, const i2v_tensor* o, int n_pos,
+                          int heads, int frames, int d, float scale, int dtype, int mode, void* stream) {
+  int rc = check_common(n_pos, heads, frames, frames, d, dtype, mode);
+  if (rc) return rc;
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  if (!q || !k || !v || !o) return fail(I2V_ERR_BAD_SHAPE, "null tensor");
+  const bool fast_ok = temporal_supported(heads, frames, d, dtype, q, k, v, o);
+  if (mode == I2V_MODE_FAST && !fast_ok)
+    return fail(I2V_ERR_UNSUPPORTED,
+                "i2v_temporal_attn_fwd: FAST path needs bf16, frames<=32, d in {16,32,40,64,80,128,160}, heads %% 8 "
+                "(d<=80) or %% 4, stride_h == d (frames=%d d=%d heads=%d)", frames, d, heads);
+  if (mode != I2V_MODE_GENERIC && fast_ok) {
+    if ((rc = check_tensor("q", q, 2, true)) || (rc = check_tensor("k", k, 2, true)) ||
+        (rc = check_tensor("v", v, 2, true)) || (rc = check_tensor("o", o, 2, true)))
+      return rc;
+    i2v::TemporalParams P;
+    P.q = (const __nv_bfloat16*)q->data; P.k = (const __nv_bfloat16*)k->data;
+    P.v = (const __nv_bfloat16*)v->data; P.o = (__nv_bfloat16*)o->data;
+    P.q_sp = q->stride_b; P.q_sf = q->stride_s; P.k_sp = k->stride_b; P.k_sf = k->stride_s;
+    P.v_sp = v->stride_b; P.v_sf = v->stride_s; P.o_sp = o->stride_b; P.o_sf = o->stride_s;
+    P.n_pos = n_pos; P.frames = frames; P.heads = heads; P.d = d;
+    P.scale_log2e = scale * 1.4426950408889634f;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d) {
+      case 16:  return launch_temporal_ft<16, 8>(P, di->sms, st);
+      case 32:  return launch_temporal_ft<32, 8>(P, di->sms, st);
+      case 40:  return launch_temporal_ft<40, 8>(P, di->sms, st);
+      case 64:  return launch_temporal_ft<64, 8>(P, di->sms, st);
+      case 80:  return launch_temporal_ft<80, 8>(P, di->sms, st);
+      case 128: return launch_temporal_ft<128, 4>(P, di->sms, st);
+      case 160: return launch_temporal_ft<160, 4>(P, di->sms, st);
+    }
+  }
+  return launch_generic(q, k, v, o, nullptr, nullptr, n_pos, heads, frames, frames, 0, d, 1, scale, 0.f, dtype,
+                        (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// frame partitioner layout kernels
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+// Copies 16-byte vectors between x[v, f, S, C] and chunks[r][v, f, S/G, C].
+__global__ void reshard_pack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int f_all,
+                                    int seq, int seq_local, int cvec, int inverse) {
+  // index space: (r, v*f, s_local, cv) over the chunked layout
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int cv = (int)(t % cvec); t /= cvec;
+    const int s = (int)(t % seq_local); t /= seq_local;
+    const long long vf = t % f_all; t /= f_all;
+    const int r = (int)t;
+    const long long full = (vf * seq + (long long)r * seq_local + s) * cvec + cv;
+    if (!inverse) dst[i] = src[full]; else dst[full] = src[i];
+  }
+}
+// Copies between recv[g][v, f, s, c] and y[v, g*f_local + f, s, c].
+__global__ void reshard_unpack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int videos,
+                                      int f_local, int world, long long inner /* seq_local * cvec */, int inverse) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const long long in = t % inner; t /= inner;
+    const int f = (int)(t % f_local); t /= f_local;
+    const int v = (int)(t % videos); t /= videos;
+    const int g = (int)t;
+    const long long y = (((long long)v * world + g) * f_local + f) * inner + in;
+    if (!inverse) dst[y] = src[i]; else dst[i] = src[y];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int i2v_reshard_pack(const void* src, void* dst, int videos, int f_local, int seq, int channels, int world, int elem_bytes,
+                     int inverse, void* stream) {
+  if (videos <= 0 || f_local <= 0 || seq <= 0 || channels <= 0 || world <= 0)
+    return fail(I2V_ERR_BAD_SHAPE, "reshard_pack: sizes must be positive");
+  if (seq % world) return fail(I2V_ERR_BAD_SHAPE, "reshard_pack: seq %d not divisible by world %d", seq, world);
+  if ((elem_bytes != 2 && elem_bytes != 4) || (channels * elem_bytes) % 16)
+    return fail(I2V_ERR_MISALIGNED, "reshard_pack: channels*elem_bytes must be a multiple of 16");
+  if (!aligned16(src) || !aligned16(dst)) return fail(I2V_ERR_MISALIGNED, "reshard_pack: pointers must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const int cvec = channels * elem_bytes / 16;
+  const long long total = (long long)videos * f_local * seq * cvec;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > (long long)di->sms * 16) blocks = (long long)di->sms * 16;
+  reshard_pack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, total,
+                                                                             videos * f_local, seq, seq / world, cvec, inverse);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int seq_local, int channels, int world,
+                       int elem_bytes, int inverse, void* stream) {
+  if (videos <= 0 || f_local <= 0 || seq_local <= 0 || channels <= 0 || world <= 0)
+    return fail(I2V_ERR_BAD_SHAPE, "reshard_unpack: sizes must be positive");
+  if ((elem_bytes != 2 && elem_bytes != 4) || (channels * elem_bytes) % 16)
+    return fail(I2V_ERR_MISALIGNED, "reshard_unpack: channels*elem_bytes must be a multiple of 16");
+  if (!aligned16(src) || !aligned16(dst)) return fail(I2V_ERR_MISALIGNED, "reshard_unpack: pointers must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const long long inner = (long long)seq_local * (channels * elem_bytes / 16);
+  const long long total = (long long)world * videos * f_local * inner;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > (long long)di->sms * 16) blocks = (long long)di->sms * 16;
+  reshard_unpack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, total,
+                                                                               videos, f_local, world, inner, inverse);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+// Dense attention forward on sm_100a: QK^T and PV on tcgen05 MMAs with TMEM accumulators, K/V tiles staged
+// by TMA into a multi-stage shared-memory ring, online softmax in registers (one thread per query row).
+//
+// One launch serves up to two independent "problems" that share the shape (batch, heads, sq, skv, d):
+//   * K1 spatial self-attention            (reference: src/modules/i2v_adapter.py:468-473)
+//   * K2 I2V-Adapter cross-frame attention (reference: src/modules/i2v_adapter.py:484-492), kv_group = num_frames so
+//     every frame of a video reads the single frame-0 K/V copy instead of the F-times repeated tensor (:485)
+//   * K3 IP-Adapter decoupled cross-attention (diffusers IPAdapterAttnProcessor2_0, installed at
+//     src/models/unet_motion_cross_frame_attn.py:1264-1279): one KV tile holding [text | image] tokens with a
+//     two-segment softmax (seg_split) and the image branch scaled by seg_scale.
+//
+// CTA = 320 threads:  warps 0-3 softmax/epilogue for query tile A (rows q0 .. q0+127)
+//                     warps 4-7 softmax/epilogue for query tile B (rows q0+128 .. q0+255)
+//                     warp 8    TMA producer,  warp 9  MMA issuer (+ TMEM allocation)
+// TMEM columns:       [0,BN) S_A / P_A   [BN,2BN) S_B / P_B   [2BN,2BN+DK) O_A   [2BN+DK,2BN+2DK) O_B
+#pragma once
+#include <cuda.h>
+#include "ptx_sm100.cuh"
+
+namespace i2v {
+
+struct DenseProblem {
+  CUtensorMap tm_q;  // dims (d, heads, sq, batch), box (64, 1, 128, 1), SWIZZLE_128B
+  CUtensorMap tm_k;  // dims (d, heads, skv, batch_kv), box (64, 1, BLOCK_N, 1)
+  CUtensorMap tm_v;
+  __nv_bfloat16* o;
+  long long o_sb, o_ss, o_sh;  // element strides: batch, sequence, head (d contiguous)
+  int kv_group;                // K/V batch index = b / kv_group
+  int pad_;
+};
+
+struct DenseParams {
+  DenseProblem prob[2];
+  int nprob;
+  int batch, heads, sq, skv, d;
+  int q_blocks;        // ceil(sq / 256)
+  float scale_log2e;   // softmax scale * log2(e)
+  int seg_split;       // <0: plain softmax. >=0: two-segment softmax (single KV tile), columns >= seg_split
+  float seg_scale;     //      form the second segment whose normalised probabilities are multiplied by seg_scale
+};
+
+template <int DK_, int BLOCK_N_, int NSTAGES_>
+struct DenseCfg {
+  static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16 (MMA K of QK^T, N of PV)
+  static constexpr int BLOCK_N = BLOCK_N_;  // keys per tile
+  static constexpr int NSTAGES = NSTAGES_;
+  static constexpr int KSUB = (DK + 63) / 64;  // 64-column (128-byte) swizzle sub-tiles per row
+  static constexpr int KSTEPS = DK / 16;
+  static constexpr int Q_SUB_BYTES = 128 * 128;
+  static constexpr int KV_SUB_BYTES = BLOCK_N * 128;
+  static constexpr int Q_TILE_BYTES = KSUB * Q_SUB_BYTES;
+  static constexpr int KV_TILE_BYTES = KSUB * KV_SUB_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_S0 = 0, TMEM_S1 = BLOCK_N, TMEM_O0 = 2 * BLOCK_N, TMEM_O1 = 2 * BLOCK_N + DK;
+  static constexpr int TMEM_COLS_USED = 2 * BLOCK_N + 2 * DK;
+  static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
+  static_assert(DK % 16 == 0 && DK >= 16 && DK <= 256, "DK");
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 128, "BLOCK_N");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+};
+
+constexpr int kDenseThreads = 320;
+constexpr float kRescaleThreshold = 8.0f;  // lazy O rescale: only when the running max grows by > 2^8
+
+template <class Cfg>
+__global__ void __launch_bounds__(kDenseThreads, 1) dense_attn_kernel(const __grid_constant__ DenseParams P) {
+  constexpr int DK = Cfg::DK, BN = Cfg::BLOCK_N, NS = Cfg::NSTAGES, KSUB = Cfg::KSUB, KSTEPS = Cfg::KSTEPS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_q = smem;                                  // [2][KSUB][128 rows][128 B]
+  uint8_t* sm_k = sm_q + 2 * Cfg::Q_TILE_BYTES;          // [NS][KSUB][BN rows][128 B]
+  uint8_t* sm_v = sm_k + NS * Cfg::KV_TILE_BYTES;        // [NS][KSUB][BN rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + NS * Cfg::KV_TILE_BYTES);
+  uint64_t* bar_q_full = bars + 0;      // [1]
+  uint64_t* bar_k_full = bars + 1;      // [NS]
+  uint64_t* bar_v_full = bars + 1 + NS; // [NS]
+  uint64_t* bar_kv_empty = bars + 1 + 2 * NS;  // [NS]
+  uint64_t* bar_s_full = bars + 1 + 3 * NS;    // [2]
+  uint64_t* bar_p_full = bars + 3 + 3 * NS;    // [2]
+  uint64_t* bar_o_full = bars + 5 + 3 * NS;    // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 7 + 3 * NS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- work decomposition: q-block fastest so the CTAs sharing one (batch, head) K/V run together ----
+  int x = blockIdx.x;
+  const int qb = x % P.q_blocks;  x /= P.q_blocks;
+  const int h = x % P.heads;      x /= P.heads;
+  const int b = x % P.batch;      x /= P.batch;
+  const int pi = x;  // problem index
+  const DenseProblem& prob = P.prob[pi];
+  const int q0 = qb * 256;
+  const bool tile_b_active = (q0 + 128) < P.sq;
+  const int ntiles = tile_b_active ? 2 : 1;
+  const int n_kv = (P.skv + BN - 1) / BN;
+  const int bkv = b / prob.kv_group;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bar_k_full + s, 1);
+      mbar_init(bar_v_full + s, 1);
+      mbar_init(bar_kv_empty + s, 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_s_full + t, 1);
+      mbar_init(bar_p_full + t, 128);
+      mbar_init(bar_o_full + t, 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) {
+    tmem_alloc<512>(tmem_base_slot);
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&prob.tm_q);
+    tma_prefetch_desc(&prob.tm_k);
+    tma_prefetch_desc(&prob.tm_v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 8) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q_full, ntiles * Cfg::Q_TILE_BYTES);
+      for (int t = 0; t < ntiles; ++t)
+        for (int ks = 0; ks < KSUB; ++ks)
+          tma_load_4d(sm_q + t * Cfg::Q_TILE_BYTES + ks * Cfg::Q_SUB_BYTES, &prob.tm_q, bar_q_full, ks * 64, h,
+                      q0 + t * 128, b, kEvictFirst);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        mbar_wait(bar_kv_empty + s, ph ^ 1);
+        mbar_arrive_expect_tx(bar_k_full + s, Cfg::KV_TILE_BYTES);
+        for (int ks = 0; ks < KSUB; ++ks)
+          tma_load_4d(sm_k + s * Cfg::KV_TILE_BYTES + ks * Cfg::KV_SUB_BYTES, &prob.tm_k, bar_k_full + s, ks * 64, h,
+                      j * BN, bkv, kEvictLast);
+        mbar_arrive_expect_tx(bar_v_full + s, Cfg::KV_TILE_BYTES);
+        for (int ks = 0; ks < KSUB; ++ks)
+          tma_load_4d(sm_v + s * Cfg::KV_TILE_BYTES + ks * Cfg::KV_SUB_BYTES, &prob.tm_v, bar_v_full + s, ks * 64, h,
+                      j * BN, bkv, kEvictLast);
+      }
+    }
+  } else if (warp == 9) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, DK, 0, 1);
+      const uint32_t q_addr = smem_u32(sm_q);
+      const uint32_t k_addr = smem_u32(sm_k);
+      const uint32_t v_addr = smem_u32(sm_v);
+      const uint32_t tm_s[2] = {tmem_base + Cfg::TMEM_S0, tmem_base + Cfg::TMEM_S1};
+      const uint32_t tm_o[2] = {tmem_base + Cfg::TMEM_O0, tmem_base + Cfg::TMEM_O1};
+
+      auto issue_qk = [&](int t, int s) {
+        const uint32_t qa = q_addr + t * Cfg::Q_TILE_BYTES;
+        const uint32_t ka = k_addr + s * Cfg::KV_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          const uint32_t sub = kk >> 2, off = (kk & 3) * 32;
+          const uint64_t da = make_smem_desc_sw128(qa + sub * Cfg::Q_SUB_BYTES + off, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(ka + sub * Cfg::KV_SUB_BYTES + off, 16, 1024);
+          umma_ss(tm_s[t], da, db, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int s, bool accumulate) {
+        const uint32_t va = v_addr + s * Cfg::KV_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          // B = V tile, MN-major: 16 key rows per k-step (2048 B), 64-column atoms KV_SUB_BYTES apart.
+          const uint64_t db = make_smem_desc_sw128(va + kk * 2048, Cfg::KV_SUB_BYTES, 1024);
+          umma_ts(tm_o[t], tm_s[t] + kk * 8, db, idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(bar_q_full, 0);
+      mbar_wait(bar_k_full + 0, 0);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) {
+        issue_qk(t, 0);
+        tc_commit(bar_s_full + t);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        const int sn = (j + 1) % NS;
+        const uint32_t phn = ((j + 1) / NS) & 1;
+        mbar_wait(bar_v_full + s, ph);
+        if (j + 1 < n_kv) mbar_wait(bar_k_full + sn, phn);
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(bar_p_full + t, j & 1);
+          tc_fence_after();
+          issue_pv(t, s, j > 0);
+          if (j + 1 < n_kv) {
+            issue_qk(t, sn);
+            tc_commit(bar_s_full + t);
+          } else {
+            tc_commit(bar_o_full + t);
+          }
+        }
+        tc_commit(bar_kv_empty + s);
+      }
+    }
+  } else {
+    // =========================== softmax + epilogue warpgroups ===========================
+    const int t = warp >> 2;             // query tile handled by this warpgroup
+    if (t < ntiles) {
+      const int row = (warp & 3) * 32 + lane;  // TMEM lane == query row within the tile
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tm_s = tmem_base + (t == 0 ? Cfg::TMEM_S0 : Cfg::TMEM_S1) + lane_addr;
+      const uint32_t tm_o = tmem_base + (t == 0 ? Cfg::TMEM_O0 : Cfg::TMEM_O1) + lane_addr;
+      const float c = P.scale_log2e;
+      float m_ref = -INFINITY;  // running reference max (in the scaled log2 domain)
+      float l = 0.f;            // running row sum
+      const bool two_seg = P.seg_split >= 0;
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(bar_s_full + t, j & 1);
+        tc_fence_after();
+        float sv[BN];
+#pragma unroll
+        for (int cch = 0; cch < BN / 32; ++cch) {
+          uint32_t r[32];
+          tmem_ld_x32(tm_s + cch * 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[cch * 32 + i] = __uint_as_float(r[i]);
+        }
+        tc_wait_ld();
+        const int valid = P.skv - j * BN;  // columns >= valid are padding
+
+        if (!two_seg) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < BN; ++i) {
+            if (i >= valid) sv[i] = -INFINITY;
+            mx = fmaxf(mx, sv[i]);
+          }
+          mx *= c;
+          // lazy rescale: keep the old reference unless the max grew by more than the threshold
+          float alpha = 1.f;
+          bool need = false;
+          if (mx > m_ref + kRescaleThreshold || m_ref == -INFINITY) {
+            alpha = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - mx);
+            m_ref = mx;
+            need = true;
+          }
+          if (j > 0 && __any_sync(0xffffffffu, need)) {
+            // correct the O accumulator of this row (PV of tile j-1 has retired: s_full(j) was committed after it)
+#pragma unroll
+            for (int cch = 0; cch < DK / 16; ++cch) {
+              uint32_t r[16];
+              tmem_ld_x16(tm_o + cch * 16, r);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_x16(tm_o + cch * 16, r);
+            }
+            tc_wait_st();
+          }
+          l *= alpha;
+          float lsum = 0.f;
+#pragma unroll
+          for (int cch = 0; cch < BN / 32; ++cch) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2_approx(fmaf(sv[cch * 32 + 2 * i], c, -m_ref));
+              const float p1 = ex2_approx(fmaf(sv[cch * 32 + 2 * i + 1], c, -m_ref));
+              lsum += p0 + p1;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_x16(tm_s + cch * 16, pk);
+          }
+          l += lsum;
+        } else {
+          // two-segment softmax over a single KV tile: [0,split) and [split,valid); probabilities are
+          // normalised here so the accumulator needs no final division.
+          const int split = P.seg_split;
+          float m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < BN; ++i) {
+            if (i < split) m1 = fmaxf(m1, sv[i]);
+            else if (i < valid) m2 = fmaxf(m2, sv[i]);
+          }
+          m1 *= c; m2 *= c;
+          float l1 = 0.f, l2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < BN; ++i) {
+            float e = 0.f;
+            if (i < split) { e = ex2_approx(fmaf(sv[i], c, -m1)); l1 += e; }
+            else if (i < valid) { e = ex2_approx(fmaf(sv[i], c, -m2)); l2 += e; }
+            sv[i] = e;
+          }
+          const float w1 = (l1 > 0.f) ? 1.f / l1 : 0.f;
+          const float w2 = (l2 > 0.f) ? P.seg_scale / l2 : 0.f;
+#pragma unroll
+          for (int cch = 0; cch < BN / 32; ++cch) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int i0 = cch * 32 + 2 * i;
+              pk[i] = pack_bf16x2(sv[i0] * (i0 < split ? w1 : w2), sv[i0 + 1] * (i0 + 1 < split ? w1 : w2));
+            }
+            tmem_st_x16(tm_s + cch * 16, pk);
+          }
+          l = 1.f;
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p_full + t);
+      }
+
+      // ---- epilogue: O / l -> bf16 -> global ----
+      mbar_wait(bar_o_full + t, 0);
+      tc_fence_after();
+      const float inv_l = 1.f / l;
+      const int qrow = q0 + t * 128 + row;
+      __nv_bfloat16* orow = prob.o + (long long)b * prob.o_sb + (long long)qrow * prob.o_ss + (long long)h * prob.o_sh;
+#pragma unroll
+      for (int cch = 0; cch < DK / 16; ++cch) {
+        uint32_t r[16];
+        tmem_ld_x16(tm_o + cch * 16, r);
+        tc_wait_ld();
+        if (qrow < P.sq) {
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const int col = cch * 16 + g8 * 8;
+            if (col < P.d) {  // d is a multiple of 8
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(r[g8 * 8 + 0]) * inv_l, __uint_as_float(r[g8 * 8 + 1]) * inv_l);
+              v.y = pack_bf16x2(__uint_as_float(r[g8 * 8 + 2]) * inv_l, __uint_as_float(r[g8 * 8 + 3]) * inv_l);
+              v.z = pack_bf16x2(__uint_as_float(r[g8 * 8 + 4]) * inv_l, __uint_as_float(r[g8 * 8 + 5]) * inv_l);
+              v.w = pack_bf16x2(__uint_as_float(r[g8 * 8 + 6]) * inv_l, __uint_as_float(r[g8 * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + col) = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace i2v

@@ -1,0 +1,207 @@
+"""Torch-facing wrappers of the C ABI (``include/i2v_attn_b200.h``).
+
+PyTorch is used for device memory and streams only: each function validates its tensors, allocates the output,
+passes raw device pointers + element strides to ``libi2v_attn_b200.so`` and returns.  The work is enqueued on
+``torch.cuda.current_stream()``; nothing synchronises.  CPU tensors are rejected — there is no fallback.
+
+The same functions are registered as ``torch.ops.i2v_b200.*`` (CUDA dispatch key only).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import I2VTensor, MODE_AUTO, MODE_FAST, MODE_GENERIC  # noqa: F401  (re-exported)
+
+_DTYPES = {torch.bfloat16: _lib.I2V_BF16, torch.float32: _lib.I2V_F32}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"i2v_b200 kernels take bfloat16 or float32 tensors, got {t.dtype}") from None
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise RuntimeError(
+                "i2v_b200 kernels run on CUDA (sm_100a) tensors only; got a tensor on "
+                f"'{t.device}'. There is no CPU fallback.")
+        if t.device != dev:
+            raise RuntimeError("all tensors must live on the same CUDA device")
+    return dev
+
+
+def _desc(t: torch.Tensor) -> I2VTensor:
+    """[b, s, h, d] view -> i2v_tensor."""
+    if t.dim() != 4:
+        raise ValueError(f"expected a 4-D [batch, seq, heads, d] view, got shape {tuple(t.shape)}")
+    if t.shape[-1] > 1 and t.stride(-1) != 1:
+        raise ValueError("the head dimension must be contiguous")
+    return I2VTensor(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+
+
+def _stream(dev: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _on_device:
+    """Make ``dev`` current for the duration of the call (cheap when it already is)."""
+
+    def __init__(self, dev: torch.device):
+        self.dev = dev
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.dev.index is not None and self.dev.index != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_group: int = 1, scale: Optional[float] = None,
+         mode: int = MODE_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B, Sq, H, d]; k, v [B / kv_group, Skv, H, d] (strided views allowed) -> o [B, Sq, H, d] contiguous."""
+    dev = _require_cuda(q, k, v)
+    B, Sq, H, d = q.shape
+    Skv = k.shape[1]
+    if k.shape != v.shape or k.shape[0] * kv_group != B or k.shape[2] != H or k.shape[3] != d:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} kv_group {kv_group}")
+    if k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError("q, k, v must share a dtype")
+    o = torch.empty((B, Sq, H, d), dtype=q.dtype, device=dev) if out is None else out
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_sdpa_fwd(_desc(q), _desc(k), _desc(v), _desc(o), B, H, Sq, Skv, d, kv_group, scale,
+                                    _dtype_code(q), mode, _stream(dev)))
+    return o
+
+
+def fused_self_xframe(q_self, k_self, v_self, q_x, k_x, v_x, num_frames: int, scale: Optional[float] = None,
+                      mode: int = MODE_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Spatial self-attention + I2V-Adapter cross-frame attention in one launch.
+
+    q_self, k_self, v_self, q_x: [B*F, S, H, d]; k_x, v_x: [B, S, H, d] (frame 0 of each video).
+    Returns o [B*F, S, 2, H, d]: o[:, :, 0] = self-attention, o[:, :, 1] = cross-frame attention, i.e. a
+    [B*F, S, 2*H*d] matrix ready for a single stacked output projection."""
+    dev = _require_cuda(q_self, k_self, v_self, q_x, k_x, v_x)
+    BF, S, H, d = q_self.shape
+    if BF % num_frames:
+        raise ValueError(f"Batch size {BF} must be divisible by the number of frames {num_frames}.")
+    o = torch.empty((BF, S, 2, H, d), dtype=q_self.dtype, device=dev) if out is None else out
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_fused_self_xframe_fwd(
+            _desc(q_self), _desc(k_self), _desc(v_self), _desc(o[:, :, 0]), _desc(q_x), _desc(k_x), _desc(v_x),
+            _desc(o[:, :, 1]), BF, H, S, d, num_frames, scale, _dtype_code(q_self), mode, _stream(dev)))
+    return o
+
+
+def ip_xattn(q, k, v, n_txt: int, ip_scale: float, kv_group: int = 1, scale: Optional[float] = None,
+             mode: int = MODE_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """IP-Adapter decoupled cross-attention.  q [B, Sq, H, d]; k, v [B / kv_group, n_txt + n_ip, H, d] hold the text
+    tokens followed by the image-prompt tokens."""
+    dev = _require_cuda(q, k, v)
+    B, Sq, H, d = q.shape
+    n_ip = k.shape[1] - n_txt
+    if n_ip <= 0 or n_txt <= 0:
+        raise ValueError(f"need text and image tokens, got n_txt={n_txt}, total={k.shape[1]}")
+    o = torch.empty((B, Sq, H, d), dtype=q.dtype, device=dev) if out is None else out
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_ip_xattn_fwd(
+            _desc(q), _desc(k[:, :n_txt]), _desc(v[:, :n_txt]), _desc(k[:, n_txt:]), _desc(v[:, n_txt:]), _desc(o),
+            B, H, Sq, n_txt, n_ip, d, kv_group, scale, float(ip_scale), _dtype_code(q), mode, _stream(dev)))
+    return o
+
+
+def temporal_attn(q, k, v, scale: Optional[float] = None, mode: int = MODE_AUTO,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q, k, v [n_pos, F, H, d] (strided views allowed, head stride == d) -> o [n_pos, F, H, d] contiguous."""
+    dev = _require_cuda(q, k, v)
+    N, Fr, H, d = q.shape
+    if k.shape != q.shape or v.shape != q.shape:
+        raise ValueError("temporal attention is self-attention: q, k, v must have the same shape")
+    o = torch.empty((N, Fr, H, d), dtype=q.dtype, device=dev) if out is None else out
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_temporal_attn_fwd(_desc(q), _desc(k), _desc(v), _desc(o), N, H, Fr, d, scale,
+                                             _dtype_code(q), mode, _stream(dev)))
+    return o
+
+
+def reshard_pack(x: torch.Tensor, world: int, inverse: bool = False, out: Optional[torch.Tensor] = None):
+    """x [V, f, S, C] -> chunks [G, V, f, S/G, C] (inverse: chunks -> x)."""
+    dev = _require_cuda(x)
+    if not x.is_contiguous():
+        raise ValueError("reshard_pack needs a contiguous tensor")
+    if not inverse:
+        V, f, S, C = x.shape
+        o = torch.empty((world, V, f, S // world, C), dtype=x.dtype, device=dev) if out is None else out
+    else:
+        G, V, f, Sl, C = x.shape
+        S = Sl * G
+        o = torch.empty((V, f, S, C), dtype=x.dtype, device=dev) if out is None else out
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_reshard_pack(x.data_ptr(), o.data_ptr(), V, f, S, C, world, x.element_size(),
+                                        int(inverse), _stream(dev)))
+    return o
+
+
+def reshard_unpack(x: torch.Tensor, world: int, inverse: bool = False, out: Optional[torch.Tensor] = None):
+    """recv [G, V, f, Sl, C] -> y [V, G*f, Sl, C] (inverse: y -> recv)."""
+    dev = _require_cuda(x)
+    if not x.is_contiguous():
+        raise ValueError("reshard_unpack needs a contiguous tensor")
+    if not inverse:
+        G, V, f, Sl, C = x.shape
+        o = torch.empty((V, G * f, Sl, C), dtype=x.dtype, device=dev) if out is None else out
+    else:
+        V, Fall, Sl, C = x.shape
+        f = Fall // world
+        o = torch.empty((world, V, f, Sl, C), dtype=x.dtype, device=dev) if out is None else out
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_reshard_unpack(x.data_ptr(), o.data_ptr(), V, f, Sl, C, world, x.element_size(),
+                                          int(inverse), _stream(dev)))
+    return o
+
+
+# ----------------------------------------------------------------------------------------------------------
+# torch.library registration: torch.ops.i2v_b200.*  (CUDA key only -> CPU tensors raise NotImplementedError)
+# ----------------------------------------------------------------------------------------------------------
+_torch_lib = None
+
+
+def register_torch_ops() -> None:
+    global _torch_lib
+    if _torch_lib is not None:
+        return
+    lib = torch.library.Library("i2v_b200", "DEF")
+    lib.define("sdpa(Tensor q, Tensor k, Tensor v, int kv_group, float scale, int mode) -> Tensor")
+    lib.define("fused_self_xframe(Tensor q_self, Tensor k_self, Tensor v_self, Tensor q_x, Tensor k_x, Tensor v_x, "
+               "int num_frames, float scale, int mode) -> Tensor")
+    lib.define("ip_xattn(Tensor q, Tensor k, Tensor v, int n_txt, float ip_scale, int kv_group, float scale, "
+               "int mode) -> Tensor")
+    lib.define("temporal_attn(Tensor q, Tensor k, Tensor v, float scale, int mode) -> Tensor")
+    lib.impl("sdpa", lambda q, k, v, g, s, m: sdpa(q, k, v, g, s, m), "CUDA")
+    lib.impl("fused_self_xframe",
+             lambda qs, ks, vs, qx, kx, vx, f, s, m: fused_self_xframe(qs, ks, vs, qx, kx, vx, f, s, m), "CUDA")
+    lib.impl("ip_xattn", lambda q, k, v, n, ips, g, s, m: ip_xattn(q, k, v, n, ips, g, s, m), "CUDA")
+    lib.impl("temporal_attn", lambda q, k, v, s, m: temporal_attn(q, k, v, s, m), "CUDA")
+    _torch_lib = lib

@@ -1,0 +1,122 @@
+/*
+ * i2v_attn_b200.h — C ABI of libi2v_attn_b200.so: the B200 (sm_100a) attention hot path of
+ * xUhEngwAng/I2V-Adapter-Unofficial.
+ *
+ * Every entry point replaces one library call the reference reaches through the diffusers AttnProcessor boundary
+ * (SURVEY.md §8b).  Reference locations are relative to /root/reference:
+ *
+ *   i2v_sdpa_fwd              F.scaled_dot_product_attention inside AttnProcessor2_0 for attn1 / i2v_adapter
+ *                             (called from src/modules/i2v_adapter.py:468-473 and :487-492)
+ *   i2v_fused_self_xframe_fwd the pair attn1 (:468-473) + i2v_adapter (:484-492) of one I2VAdapterTransformerBlock
+ *                             in a single launch; the frame-0 K/V are indexed in place instead of being
+ *                             repeated num_frames times (einops.repeat at :485)
+ *   i2v_ip_xattn_fwd          the two SDPA calls + scaled add of IPAdapterAttnProcessor2_0, installed at
+ *                             src/models/unet_motion_cross_frame_attn.py:1264-1279, tokens built at :1346-1355
+ *   i2v_temporal_attn_fwd     SDPA of the motion-module attn1/attn2 (TransformerTemporalModel constructed at
+ *                             src/models/unet_motion_cross_frame_attn.py:232-244, called at :323-326)
+ *   i2v_reshard_*             layout kernels of the frame partitioner (new functionality)
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device; `stream` is a cudaStream_t (NULL = legacy default);
+ *   - tensors are logical [batch, seq, heads, d] with d contiguous and element strides (stride_b, stride_s, stride_h),
+ *     exactly the view the reference takes of a Linear output: `.view(B, -1, heads, head_dim)`;
+ *   - work is only enqueued, never synchronised; outputs are written in full (never accumulated);
+ *   - return value 0 on success, a negative i2v_status otherwise; i2v_last_error() gives the message for the calling
+ *     thread.  Nothing aborts and nothing falls back to the CPU.
+ */
+#ifndef I2V_ATTN_B200_H
+#define I2V_ATTN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  I2V_OK = 0,
+  I2V_ERR_BAD_SHAPE = -1,       /* non-positive sizes, batch not divisible by kv_group / num_frames, ... */
+  I2V_ERR_UNSUPPORTED = -2,     /* shape or dtype outside what the requested kernel family covers */
+  I2V_ERR_MISALIGNED = -3,      /* pointer not 16-byte aligned or stride not a multiple of 8 elements */
+  I2V_ERR_CUDA = -4,            /* a CUDA runtime / driver call failed (message has the CUDA error string) */
+  I2V_ERR_BAD_DTYPE = -5,
+  I2V_ERR_NO_DEVICE = -6        /* current device is not compute capability 10.x */
+} i2v_status;
+
+typedef enum { I2V_BF16 = 0, I2V_F32 = 1 } i2v_dtype;
+
+/* Kernel family selection.
+ *   AUTO   : tensor-core / bandwidth kernel when the shape is covered and dtype is bf16, else GENERIC
+ *   FAST   : tensor-core / bandwidth kernel or I2V_ERR_UNSUPPORTED
+ *   GENERIC: CUDA-core kernel with fp32 math ("fp32 check mode"; bf16 or fp32 storage) */
+typedef enum { I2V_MODE_AUTO = 0, I2V_MODE_FAST = 1, I2V_MODE_GENERIC = 2 } i2v_mode;
+
+typedef struct {
+  void* data;
+  int64_t stride_b; /* elements between consecutive batch entries   */
+  int64_t stride_s; /* elements between consecutive sequence rows   */
+  int64_t stride_h; /* elements between consecutive heads           */
+} i2v_tensor;
+
+int i2v_version(void);
+const char* i2v_last_error(void);
+/* 1 if the current device can run the sm_100a kernels, 0 otherwise (and sets the error string). */
+int i2v_device_supported(void);
+/* Number of kernels this library has launched in this process (evidence for bench.py's gpu_launches). */
+int64_t i2v_launch_count(void);
+
+/* o[b,:,h,:] = softmax(scale * q[b,:,h,:] k[b/kv_group,:,h,:]^T) v[b/kv_group,:,h,:]
+ * k, v hold batch/kv_group entries.  kv_group = 1 is ordinary (self or cross) attention. */
+int i2v_sdpa_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_tensor* v, const i2v_tensor* o,
+                 int batch, int heads, int sq, int skv, int d, int kv_group, float scale,
+                 int dtype, int mode, void* stream);
+
+/* Spatial self-attention and I2V-Adapter cross-frame attention of one block in one launch.
+ *   o_self[b] = softmax(scale q_self[b] k_self[b]^T) v_self[b]                      b in [0, batch)
+ *   o_x[b]    = softmax(scale q_x[b]    k_x[b/num_frames]^T) v_x[b/num_frames]
+ * batch = videos * num_frames, frame index fastest (batch row = video * num_frames + frame, as produced by
+ * src/models/unet_motion_cross_frame_attn.py:1358); k_x, v_x hold one entry per video (frame 0's projection). */
+int i2v_fused_self_xframe_fwd(const i2v_tensor* q_self, const i2v_tensor* k_self, const i2v_tensor* v_self,
+                              const i2v_tensor* o_self, const i2v_tensor* q_x, const i2v_tensor* k_x,
+                              const i2v_tensor* v_x, const i2v_tensor* o_x,
+                              int batch, int heads, int seq, int d, int num_frames, float scale,
+                              int dtype, int mode, void* stream);
+
+/* IP-Adapter decoupled cross-attention:
+ *   o = softmax(scale q k_txt^T) v_txt + ip_scale * softmax(scale q k_ip^T) v_ip
+ * k/v tensors hold batch/kv_group entries (text and image tokens are identical for the frames of a video:
+ * repeat_interleave at src/models/unet_motion_cross_frame_attn.py:1355).  The FAST path needs the image tokens to
+ * directly follow the text tokens in memory (k_ip.data == &k_txt[.., n_txt, ..], same strides) and
+ * n_txt + n_ip <= 128. */
+int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_tensor* v_txt,
+                     const i2v_tensor* k_ip, const i2v_tensor* v_ip, const i2v_tensor* o,
+                     int batch, int heads, int sq, int n_txt, int n_ip, int d, int kv_group,
+                     float scale, float ip_scale, int dtype, int mode, void* stream);
+
+/* Temporal self-attention over `frames` at every spatial position.
+ * Tensors are logical [n_pos, frames, heads, d]: stride_b = position stride, stride_s = frame stride.
+ * FAST path: bf16, frames <= 32, d % 8 == 0, heads % 8 == 0 (d <= 80) or heads % 4 == 0 (d <= 160),
+ * stride_h == d. */
+int i2v_temporal_attn_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_tensor* v, const i2v_tensor* o,
+                          int n_pos, int heads, int frames, int d, float scale,
+                          int dtype, int mode, void* stream);
+
+/* Frame partitioner layout kernels (new functionality: the reference has no inference-time
+ * sharding).  A rank holding f_local frames of every video re-shards [videos, f_local, S, C] activations to
+ * [videos, F, S/G, C] (all frames, 1/G of the spatial positions) with one NCCL all-to-all between two copies:
+ *   pack   (inverse = 0): send[r][v, f, s, c]      = x[v, f, r*S/G + s, c]          r in [0, G)
+ *   unpack (inverse = 0): y[v, g*f_local + f, s, c] = recv[g][v, f, s, c]            g in [0, G)
+ * inverse = 1 runs the same index maps backwards (src and dst swap roles) for the way back.
+ * elem_bytes is 2 or 4; seq must be divisible by world; channels*elem_bytes must be a multiple of 16. */
+int i2v_reshard_pack(const void* src, void* dst, int videos, int f_local, int seq, int channels, int world,
+                     int elem_bytes, int inverse, void* stream);
+int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int seq_local, int channels, int world,
+                       int elem_bytes, int inverse, void* stream);
+
+/* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM. */
+int i2v_set_tuning(int key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2V_ATTN_B200_H */
