@@ -1,0 +1,383 @@
+"""Benchmark of BASELINE.json's metric: UNet denoise steps/s (16 frames, 512x512 -> 64x64 latent, CFG) with the
+attention hot path on the sm_100a kernels.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pipeline denoise iteration (reference src/pipelines/pipeline_i2v_adapter.py:666-691): first-frame
+re-imposition, CFG duplication, UNetMotionCrossFrameAttnModel forward (full SD1.5 architecture + motion modules +
+I2V-Adapter + IP-Adapter, random init), guidance, DDIM update.  Workload = BASELINE.json configs[1]
+(1 video x CFG, 16 frames, 64x64 latent, bf16).  N > 1: every rank samples its own video (independent videos need no
+communication) -> weak scaling, value = videos-steps per second over all ranks.
+
+The printed JSON line carries `value` (device-resident inputs), `e2e` (host buffers, H2D/D2H inside the timed
+region), `roofline` for the dominant kernel (fused spatial + cross-frame attention at level 0, timed live with CUDA
+events), `cpu_baseline` (the CPU oracle port on a bounded sample, rank 0, N = 1) and `clocks`.
+
+`--impl reference` times the reference path's CPU restatement (oracle/) with all host threads on a bounded sample of
+the same workload; the reference itself cannot run here because its `diffusers` dependency is not installable.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "UNet denoise steps/s (16f 512^2, CFG)"
+UNIT = "steps/s"
+FRAMES, LATENT, GUIDANCE, DDIM_STEPS = 16, 64, 7.5, 25
+SD15 = dict(block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, cross_attention_dim=768,
+            num_attention_heads=8, motion_num_attention_heads=8, motion_max_seq_length=32, norm_num_groups=32)
+IMAGE_EMBED_DIM = 1024
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=p.get("bf16_tflops_sustained", 1396.3), hbm=p.get("hbm_gbs", 6546.9), source="measured")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# model + inputs
+# ------------------------------------------------------------------------------------------------------------
+def build_unet(device, dtype):
+    import torch
+    from i2v_adapter_unofficial_b200.hostmodel import UNetMotionCrossFrameAttnModel
+
+    torch.manual_seed(0)
+    with torch.device(device):
+        unet = UNetMotionCrossFrameAttnModel(**SD15)
+    unet = unet.to(dtype).eval()
+    # IP-Adapter weights in the ip-adapter_sd15.bin layout, random values (there is no network for checkpoints)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    cross = SD15["cross_attention_dim"]
+    sd = {"image_proj": {"proj.weight": torch.randn(4 * cross, IMAGE_EMBED_DIM, generator=g) * IMAGE_EMBED_DIM**-0.5,
+                         "proj.bias": torch.zeros(4 * cross), "norm.weight": torch.ones(cross),
+                         "norm.bias": torch.zeros(cross)}, "ip_adapter": {}}
+    key_id = 1
+    for name in unet.attn_processors.keys():
+        if name.endswith("attn2.processor") and "motion_modules" not in name:
+            if name.startswith("mid_block"):
+                hidden = SD15["block_out_channels"][-1]
+            elif name.startswith("up_blocks"):
+                hidden = list(reversed(SD15["block_out_channels"]))[int(name[len("up_blocks.")])]
+            else:
+                hidden = SD15["block_out_channels"][int(name[len("down_blocks.")])]
+            sd["ip_adapter"][f"{key_id}.to_k_ip.weight"] = torch.randn(hidden, cross, generator=g) * cross**-0.5
+            sd["ip_adapter"][f"{key_id}.to_v_ip.weight"] = torch.randn(hidden, cross, generator=g) * cross**-0.5
+            key_id += 2
+    unet._load_ip_adapter_weights(sd)
+    return unet
+
+
+def make_inputs(videos, frames, latent, seed, dtype, device="cpu", pin=False):
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    t = dict(latents=torch.randn(videos, frames, 4, latent, latent, generator=g),
+             cond=torch.randn(videos, 4, latent, latent, generator=g),
+             prompt=torch.randn(2 * videos, 77, SD15["cross_attention_dim"], generator=g),
+             image=torch.randn(2 * videos, IMAGE_EMBED_DIM, generator=g))
+    t = {k: v.to(dtype) for k, v in t.items()}
+    if pin:
+        t = {k: v.pin_memory() for k, v in t.items()}
+    if device != "cpu":
+        t = {k: v.to(device) for k, v in t.items()}
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# ------------------------------------------------------------------------------------------------------------
+CPU_SAMPLE_FRAMES = 2
+
+
+def cpu_reference_run(steps, warmup):
+    """Times `denoise_step_oracle` (fp32, all host threads) on CPU_SAMPLE_FRAMES of the 16 frames of the workload.
+    Frames are folded into the UNet batch (reference :1358) and every operator except the temporal attention
+    (< 1 % of the FLOPs) costs the same per frame, so steps/s scale by CPU_SAMPLE_FRAMES / 16."""
+    import torch
+    import oracle.attention_oracle as attention_oracle
+    from oracle.unet_oracle import denoise_step_oracle, ddim_timesteps_oracle
+
+    attention_oracle.USE_TORCH_SDPA = True  # time the library call the reference makes (AttnProcessor2_0)
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    unet = build_unet("cpu", torch.float32)
+    sd = {k: v for k, v in unet.state_dict().items()}
+    cfg = dict(unet.config)
+    inp = make_inputs(1, CPU_SAMPLE_FRAMES, LATENT, seed=1, dtype=torch.float32)
+    ts = ddim_timesteps_oracle(DDIM_STEPS)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            denoise_step_oracle(sd, cfg, inp["latents"], int(ts[i % len(ts)]), inp["prompt"], DDIM_STEPS, GUIDANCE,
+                                inp["cond"], inp["image"])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sec_per_sample = sum(times) / len(times)
+    sec_per_step = sec_per_sample * (FRAMES / CPU_SAMPLE_FRAMES)
+    return dict(value=1.0 / sec_per_step, unit=UNIT, cores=cores, kind="port",
+                sample=(f"oracle denoise step (fp32, CFG batch 2, 64x64 latent) on {CPU_SAMPLE_FRAMES} of {FRAMES} frames, "
+                        f"{len(times)} timed iteration(s) of {sec_per_sample:.2f} s, scaled x{FRAMES // CPU_SAMPLE_FRAMES}")), \
+        sec_per_sample
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 2))
+    warmup = max(0, min(args.warmup, 1))
+    base, sec = cpu_reference_run(steps, warmup)
+    line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
+                ms_per_step=1e3 / base["value"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="configs[1]: SD1.5 UNetMotion + motion adapter + I2V-Adapter + IP-Adapter, "
+                                     "1 video x CFG, 16 frames, 64x64 latent, DDIM 25",
+                            note="reference path restated in oracle/ (diffusers not installable); CPU, bounded sample"),
+                cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+class DominantKernelTimer:
+    """CUDA-event pairs around the level-0 fused self + cross-frame attention launches (the dominant kernel)."""
+
+    def __init__(self, ops_mod, seq):
+        self.ops = ops_mod
+        self.seq = seq
+        self.pairs = []
+        self.enabled = False
+        self._orig = ops_mod.fused_self_xframe
+
+    def install(self):
+        import torch
+
+        def wrapped(q_self, *a, **kw):
+            if self.enabled and q_self.shape[1] == self.seq:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = self._orig(q_self, *a, **kw)
+                e1.record()
+                self.pairs.append((e0, e1, q_self.shape))
+                return out
+            return self._orig(q_self, *a, **kw)
+
+        self.ops.fused_self_xframe = wrapped
+
+    def summary(self):
+        if not self.pairs:
+            return None
+        ms = [a.elapsed_time(b) for a, b, _ in self.pairs]
+        bf, s, h, d = self.pairs[0][2]
+        flops = 2 * 4.0 * bf * h * s * s * d  # self + cross-frame, true head dim, softmax not counted
+        return dict(avg_ms=sum(ms) / len(ms), launches=len(ms), flops_per_launch=flops)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from i2v_adapter_unofficial_b200 import _lib, install, ops
+    from i2v_adapter_unofficial_b200.hostmodel import DDIMScheduler, denoise_step
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    dtype = torch.bfloat16
+    unet = build_unet(dev, dtype)
+    handle = install(unet)
+    sched = DDIMScheduler()
+    sched.set_timesteps(DDIM_STEPS, device="cpu")
+    ts = [int(t) for t in sched.timesteps]
+
+    timer = DominantKernelTimer(ops, LATENT * LATENT)
+    timer.install()
+
+    host = make_inputs(1, FRAMES, LATENT, seed=1 + rank, dtype=dtype, pin=True)
+    d_in = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i, latents):
+        return denoise_step(unet, sched, latents, ts[i % len(ts)], d_in["prompt"], GUIDANCE, d_in["cond"], d_in["image"])
+
+    # ---- value: inputs resident in HBM ----
+    lat = d_in["latents"].clone()
+    for i in range(args.warmup):
+        lat = one_step(i, lat)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    timer.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        lat = one_step(args.warmup + i, lat)
+    e1.record()
+    barrier()
+    timer.enabled = False
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+
+    # ---- e2e: host buffers in, host buffer out, copies inside the timed region ----
+    out_host = torch.empty_like(host["latents"]).pin_memory()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("latents", "cond", "prompt", "image"))
+    d2h = out_host.numel() * out_host.element_size()
+
+    def e2e_step(i):
+        din = {k: host[k].to(dev, non_blocking=True) for k in ("latents", "cond", "prompt", "image")}
+        new = denoise_step(unet, sched, din["latents"], ts[i % len(ts)], din["prompt"], GUIDANCE, din["cond"],
+                           din["image"])
+        out_host.copy_(new, non_blocking=True)
+
+    for i in range(min(args.warmup, 2)):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms_total = ms2.item()
+
+    if rank != 0:
+        return
+    peaks = _peaks()
+    value = world * args.steps / (ms_total / 1e3)
+    e2e_value = world * args.steps / (e2e_ms_total / 1e3)
+    dom = timer.summary()
+    roofline = None
+    if dom is not None:
+        achieved = dom["flops_per_launch"] / (dom["avg_ms"] * 1e-3) / 1e12
+        roofline = dict(bound="tensor", kernel="dense_attn_kernel<DK=48> (fused spatial self + cross-frame, level 0: "
+                        "S=4096, d=40, 32 frames x 8 heads x 2 problems)", achieved=achieved, peak=peaks["tflops"],
+                        unit="TFLOP/s", frac=achieved / peaks["tflops"], peak_source=f"{peaks['source']} sustained bf16",
+                        frac_of_nominal_2250=achieved / 2250.0, avg_launch_ms=dom["avg_ms"],
+                        launches_timed=dom["launches"], flops_per_launch=dom["flops_per_launch"], traffic=None)
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        handle.uninstall()
+        del unet
+        torch.cuda.empty_cache()
+        cpu_base, _ = cpu_reference_run(1, 0)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16", data="synthetic",
+                config=dict(workload="configs[1]: SD1.5 UNetMotion (Realistic Vision arch, random init) + motion "
+                                     "adapter + I2V-Adapter + IP-Adapter, 1 video x CFG per GPU, 16 frames, 64x64 "
+                                     "latent, DDIM 25 timesteps",
+                            parallelism=f"dp{world} (independent videos, no collective)",
+                            l2="working set >> 126 MB L2 (2.7 GB bf16 weights, 84 MB activations per level-0 tensor)"),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_base, clocks=clocks)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

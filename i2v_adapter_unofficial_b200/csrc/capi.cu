@@ -242,16 +242,18 @@ int check_common(int batch, int heads, int sq, int skv, int d, int dtype, int mo
 template <int D, int HG, int FT>
 int launch_temporal_cfg(const i2v::TemporalParams& P, int sms, cudaStream_t stream) {
   using Cfg = i2v::TemporalCfg<D, HG, FT>;
-  int stages = g_tuning[0] > 0 ? g_tuning[0] : 4;
-  const int budget = 200 * 1024;
-  while (stages > 2 && stages * Cfg::STAGE_BYTES + 256 > budget) --stages;
+  // Two co-resident CTAs per SM (16 consumer warps) when two 2..3-stage rings fit; otherwise one CTA with up to 4 stages.
+  const int budget = 226 * 1024;
+  const int ring_overhead = 256 + 128;
+  int per_sm = g_tuning[1] > 0 ? g_tuning[1] : ((2 * (2 * Cfg::STAGE_BYTES + ring_overhead + 1024) <= budget) ? 2 : 1);
+  int stages = g_tuning[0] > 0 ? g_tuning[0] : (per_sm >= 2 ? 3 : 4);
+  while (stages > 2 && per_sm * (stages * Cfg::STAGE_BYTES + ring_overhead + 1024) > budget) --stages;
   if (stages > 8) stages = 8;
-  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + 256 + 128;
+  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + ring_overhead;
   if (smem > 227 * 1024) return fail(I2V_ERR_UNSUPPORTED, "temporal stage (%d B) does not fit shared memory", Cfg::STAGE_BYTES);
   auto kern = i2v::temporal_attn_kernel<D, HG, FT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long units = (long long)P.n_pos * (P.heads / HG);
-  const int per_sm = g_tuning[1] > 0 ? g_tuning[1] : 1;
   long long grid = (long long)sms * per_sm;
   if (grid > units) grid = units;
   kern<<<(unsigned)grid, i2v::kTemporalThreads, smem, stream>>>(P, stages);
@@ -260,18 +262,20 @@ int launch_temporal_cfg(const i2v::TemporalParams& P, int sms, cudaStream_t stre
   return 0;
 }
 
-template <int D, int HG>
+// heads per staged unit: keep a stage (3 slabs of FT*16 rows) around 32-64 KB so >= 2 stages always fit
+template <int D, int FT> struct TemporalHG { static constexpr int value = (FT == 1) ? (D <= 80 ? 8 : 4) : (D <= 40 ? 8 : (D <= 80 ? 4 : 2)); };
+
+template <int D>
 int launch_temporal_ft(const i2v::TemporalParams& P, int sms, cudaStream_t stream) {
-  if (P.frames <= 16) return launch_temporal_cfg<D, HG, 1>(P, sms, stream);
-  return launch_temporal_cfg<D, HG, 2>(P, sms, stream);
+  if (P.frames <= 16) return launch_temporal_cfg<D, TemporalHG<D, 1>::value, 1>(P, sms, stream);
+  return launch_temporal_cfg<D, TemporalHG<D, 2>::value, 2>(P, sms, stream);
 }
 
 bool temporal_supported(int heads, int frames, int d, int dtype, const i2v_tensor* q, const i2v_tensor* k,
                         const i2v_tensor* v, const i2v_tensor* o) {
   if (dtype != I2V_BF16 || frames > 32) return false;
   if (!(d == 16 || d == 32 || d == 40 || d == 64 || d == 80 || d == 128 || d == 160)) return false;
-  const int hg = d <= 80 ? 8 : 4;
-  if (heads % hg) return false;
+  if (heads % 8) return false;
   if (q->stride_h != d || k->stride_h != d || v->stride_h != d || o->stride_h != d) return false;
   return true;
 }
@@ -380,8 +384,8 @@ int i2v_temporal_attn_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_te
   const bool fast_ok = temporal_supported(heads, frames, d, dtype, q, k, v, o);
   if (mode == I2V_MODE_FAST && !fast_ok)
     return fail(I2V_ERR_UNSUPPORTED,
-                "i2v_temporal_attn_fwd: FAST path needs bf16, frames<=32, d in {16,32,40,64,80,128,160}, heads %% 8 "
-                "(d<=80) or %% 4, stride_h == d (frames=%d d=%d heads=%d)", frames, d, heads);
+                "i2v_temporal_attn_fwd: FAST path needs bf16, frames<=32, d in {16,32,40,64,80,128,160}, heads %% 8 == 0, "
+                "stride_h == d (frames=%d d=%d heads=%d)", frames, d, heads);
   if (mode != I2V_MODE_GENERIC && fast_ok) {
     if ((rc = check_tensor("q", q, 2, true)) || (rc = check_tensor("k", k, 2, true)) ||
         (rc = check_tensor("v", v, 2, true)) || (rc = check_tensor("o", o, 2, true)))
@@ -395,13 +399,13 @@ int i2v_temporal_attn_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_te
     P.scale_log2e = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
     switch (d) {
-      case 16:  return launch_temporal_ft<16, 8>(P, di->sms, st);
-      case 32:  return launch_temporal_ft<32, 8>(P, di->sms, st);
-      case 40:  return launch_temporal_ft<40, 8>(P, di->sms, st);
-      case 64:  return launch_temporal_ft<64, 8>(P, di->sms, st);
-      case 80:  return launch_temporal_ft<80, 8>(P, di->sms, st);
-      case 128: return launch_temporal_ft<128, 4>(P, di->sms, st);
-      case 160: return launch_temporal_ft<160, 4>(P, di->sms, st);
+      case 16:  return launch_temporal_ft<16>(P, di->sms, st);
+      case 32:  return launch_temporal_ft<32>(P, di->sms, st);
+      case 40:  return launch_temporal_ft<40>(P, di->sms, st);
+      case 64:  return launch_temporal_ft<64>(P, di->sms, st);
+      case 80:  return launch_temporal_ft<80>(P, di->sms, st);
+      case 128: return launch_temporal_ft<128>(P, di->sms, st);
+      case 160: return launch_temporal_ft<160>(P, di->sms, st);
     }
   }
   return launch_generic(q, k, v, o, nullptr, nullptr, n_pos, heads, frames, frames, 0, d, 1, scale, 0.f, dtype,

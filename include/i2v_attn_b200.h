@@ -95,8 +95,7 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
 
 /* Temporal self-attention over `frames` at every spatial position.
  * Tensors are logical [n_pos, frames, heads, d]: stride_b = position stride, stride_s = frame stride.
- * FAST path: bf16, frames <= 32, d % 8 == 0, heads % 8 == 0 (d <= 80) or heads % 4 == 0 (d <= 160),
- * stride_h == d. */
+ * FAST path: bf16, frames <= 32, d in {16,32,40,64,80,128,160}, heads % 8 == 0, stride_h == d. */
 int i2v_temporal_attn_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_tensor* v, const i2v_tensor* o,
                           int n_pos, int heads, int frames, int d, float scale,
                           int dtype, int mode, void* stream);

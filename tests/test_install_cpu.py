@@ -1,0 +1,86 @@
+"""install(): processor mapping, IP-Adapter weight adoption, hooks, uninstall — host logic, CPU only."""
+import pytest
+import torch
+
+from helpers import TINY_CFG, make_unet
+from i2v_adapter_unofficial_b200 import (
+    B200AttnProcessor,
+    B200CrossFrameAttnProcessor,
+    B200IPAdapterAttnProcessor,
+    B200SpatialAttnProcessor,
+    B200TemporalAttnProcessor,
+    install,
+)
+from i2v_adapter_unofficial_b200.hostmodel import AttnProcessor2_0, IPAdapterAttnProcessor2_0
+from i2v_adapter_unofficial_b200.processors import _PackedWeights
+
+
+@pytest.mark.parametrize("ip", [False, True])
+def test_install_maps_every_processor(ip):
+    unet = make_unet({**TINY_CFG, "layers_per_block": 2}, ip_adapter=ip)
+    old = dict(unet.attn_processors)
+    handle = install(unet)
+    new = unet.attn_processors
+    assert list(new.keys()) == list(old.keys()) and len(new) == 90
+    counts = {}
+    for name, proc in new.items():
+        counts[type(proc).__name__] = counts.get(type(proc).__name__, 0) + 1
+        if "motion_modules" in name:
+            assert isinstance(proc, B200TemporalAttnProcessor)
+        elif name.endswith("attn1.processor"):
+            assert isinstance(proc, B200SpatialAttnProcessor) and proc.sibling is not None
+        elif name.endswith("i2v_adapter.processor"):
+            assert isinstance(proc, B200CrossFrameAttnProcessor)
+        elif ip:
+            assert isinstance(proc, B200IPAdapterAttnProcessor)
+            assert proc.to_k_ip.weight is old[name].to_k_ip.weight  # parameters shared, not copied
+        else:
+            assert type(proc) is B200AttnProcessor
+    assert counts["B200TemporalAttnProcessor"] == 42 and counts["B200SpatialAttnProcessor"] == 16
+    handle.uninstall()
+    restored = unet.attn_processors
+    for name in old:
+        assert restored[name] is old[name]
+    assert isinstance(restored["down_blocks.0.motion_modules.0.transformer_blocks.0.attn1.processor"], AttnProcessor2_0)
+
+
+def test_installed_processors_fail_loudly_on_cpu():
+    unet = make_unet()
+    install(unet)
+    x = torch.randn(1, 2, 4, 16, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        unet(x, 10, True, torch.randn(1, 5, TINY_CFG["cross_attention_dim"]))
+
+
+def test_block_hooks_carry_num_frames_and_enable_flag():
+    unet = make_unet()
+    handle = install(unet)
+    seen = {}
+    blk = unet.down_blocks[0].attentions[0].transformer_blocks[0]
+    proc = blk.attn1.processor
+
+    def spy(attn, hidden_states, **kw):
+        seen["enable"], seen["frames"] = proc.state.enable_cross_frame, proc.state.num_frames
+        raise KeyboardInterrupt  # stop before any kernel is needed
+
+    blk.attn1.processor = spy
+    with pytest.raises(KeyboardInterrupt):
+        unet(torch.randn(1, 3, 4, 16, 16), 10, True, torch.randn(1, 5, TINY_CFG["cross_attention_dim"]))
+    assert seen == {"enable": True, "frames": 3}
+    assert handle.context.num_frames == 3 and handle.context.ctx_replicated
+
+
+def test_packed_weight_cache_invalidates_on_update():
+    w = torch.nn.Parameter(torch.randn(4, 4))
+    cache = _PackedWeights()
+    calls = []
+    build = lambda: calls.append(1) or w.detach().clone()  # noqa: E731
+    a = cache.get([w], build)
+    assert cache.get([w], build) is a and len(calls) == 1
+    with torch.no_grad():
+        w.add_(1.0)  # in-place update bumps the version counter (load_state_dict does the same)
+    b = cache.get([w], build)
+    assert len(calls) == 2 and not torch.equal(a, b)
+    w.data = torch.randn(4, 4)  # storage replaced (.to(), new checkpoint)
+    cache.get([w], build)
+    assert len(calls) == 3
