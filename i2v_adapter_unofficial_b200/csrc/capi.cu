@@ -173,12 +173,24 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
     P.prob[i].o_sb = s.o->stride_b; P.prob[i].o_ss = s.o->stride_s; P.prob[i].o_sh = s.o->stride_h;
     P.prob[i].kv_group = s.kv_group;
   }
+  // g_tuning[2]: exp2-emulation split override for experiments (pairs out of 8 on the FMA pipe); 0 = default
+  const int emu = g_tuning[2] > 0 ? g_tuning[2] - 1 : -1;
   switch (dk) {
     case 16:  return launch_dense_cfg<i2v::DenseCfg<16, 128, 4>>(P, stream);
     case 32:  return launch_dense_cfg<i2v::DenseCfg<32, 128, 4>>(P, stream);
-    case 48:  return launch_dense_cfg<i2v::DenseCfg<48, 128, 4>>(P, stream);
-    case 64:  return launch_dense_cfg<i2v::DenseCfg<64, 128, 4>>(P, stream);
-    case 80:  return launch_dense_cfg<i2v::DenseCfg<80, 128, 2>>(P, stream);
+    case 48:
+      switch (emu) {
+        case 0:  return launch_dense_cfg<i2v::DenseCfg<48, 128, 4, 0>>(P, stream);
+        case 2:  return launch_dense_cfg<i2v::DenseCfg<48, 128, 4, 2>>(P, stream);
+        case 4:  return launch_dense_cfg<i2v::DenseCfg<48, 128, 4, 4>>(P, stream);
+        default: return launch_dense_cfg<i2v::DenseCfg<48, 128, 4, 3>>(P, stream);
+      }
+    case 64:  return launch_dense_cfg<i2v::DenseCfg<64, 128, 4, 2>>(P, stream);
+    case 80:
+      switch (emu) {
+        case 0:  return launch_dense_cfg<i2v::DenseCfg<80, 128, 2, 0>>(P, stream);
+        default: return launch_dense_cfg<i2v::DenseCfg<80, 128, 2, 2>>(P, stream);
+      }
     case 96:  return launch_dense_cfg<i2v::DenseCfg<96, 128, 2>>(P, stream);
     case 128: return launch_dense_cfg<i2v::DenseCfg<128, 128, 2>>(P, stream);
     case 160: return launch_dense_cfg<i2v::DenseCfg<160, 64, 2>>(P, stream);

@@ -39,8 +39,12 @@ struct DenseParams {
   float seg_scale;     //      form the second segment whose normalised probabilities are multiplied by seg_scale
 };
 
-template <int DK_, int BLOCK_N_, int NSTAGES_>
+// EMU_ = how many of every 8 (key, key+1) pairs get their 2^x from the FMA-pipe polynomial instead of MUFU.EX2.
+// At d = 40 the kernel is exp-bound (16384 exps per 128x128 tile at 16 MUFU/clk/SM = 1024 clk against 384 clk of
+// MMA), so part of the exponentials is moved to the otherwise idle FMA pipe.
+template <int DK_, int BLOCK_N_, int NSTAGES_, int EMU_ = 0>
 struct DenseCfg {
+  static constexpr int EMU = EMU_;
   static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16 (MMA K of QK^T, N of PV)
   static constexpr int BLOCK_N = BLOCK_N_;  // keys per tile
   static constexpr int NSTAGES = NSTAGES_;
@@ -235,13 +239,21 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_attn_kernel(const __gr
         const int valid = P.skv - j * BN;  // columns >= valid are padding
 
         if (!two_seg) {
-          float mx = -INFINITY;
+          if (valid < BN) {  // ragged last tile only (warp-uniform)
 #pragma unroll
-          for (int i = 0; i < BN; ++i) {
-            if (i >= valid) sv[i] = -INFINITY;
-            mx = fmaxf(mx, sv[i]);
+            for (int i = 0; i < BN; ++i)
+              if (i >= valid) sv[i] = -INFINITY;
           }
-          mx *= c;
+          // row max: 4 independent FMNMX3 chains
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < BN; i += 8) {
+            mx0 = fmax3(mx0, sv[i + 0], sv[i + 1]);
+            mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+            mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]);
+            mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
+          }
+          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
           // lazy rescale: keep the old reference unless the max grew by more than the threshold
           float alpha = 1.f;
           bool need = false;
@@ -264,20 +276,34 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_attn_kernel(const __gr
             tc_wait_st();
           }
           l *= alpha;
-          float lsum = 0.f;
+          const uint64_t c2 = f2_pack(c, c);
+          const uint64_t nm2 = f2_pack(-m_ref, -m_ref);
+          uint64_t ls0 = 0ull, ls1 = 0ull;  // two packed partial row sums
+          const bool allow_emu = valid >= BN;  // -inf padding must go through MUFU (ex2(-inf) = 0)
 #pragma unroll
           for (int cch = 0; cch < BN / 32; ++cch) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2_approx(fmaf(sv[cch * 32 + 2 * i], c, -m_ref));
-              const float p1 = ex2_approx(fmaf(sv[cch * 32 + 2 * i + 1], c, -m_ref));
-              lsum += p0 + p1;
+              const uint64_t x = f2_fma(f2_pack(sv[cch * 32 + 2 * i], sv[cch * 32 + 2 * i + 1]), c2, nm2);
+              uint64_t p2;
+              if ((i & 7) < Cfg::EMU && allow_emu) {
+                p2 = ex2_emulated_pair(x);
+              } else {
+                float x0, x1;
+                f2_unpack(x, x0, x1);
+                p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+              }
+              if (i & 1) ls1 = f2_add(ls1, p2); else ls0 = f2_add(ls0, p2);
+              float p0, p1;
+              f2_unpack(p2, p0, p1);
               pk[i] = pack_bf16x2(p0, p1);
             }
             tmem_st_x16(tm_s + cch * 16, pk);
           }
-          l += lsum;
+          float a0, a1;
+          f2_unpack(f2_add(ls0, ls1), a0, a1);
+          l += a0 + a1;
         } else {
           // two-segment softmax over a single KV tile: [0,split) and [split,valid); probabilities are
           // normalised here so the accumulator needs no final division.

@@ -239,6 +239,63 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes per FMA-pipe issue) and 3-input max (FMNMX3) ----
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0,%1,%2,%3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add_rm(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rm.f32x2 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// 2^x for a pair of x <= 0 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [0,1), degree-3
+// minimax polynomial for 2^f (max relative error 8.6e-5, far below the bf16 rounding of P), exponent patched in
+// with an integer add.  x is clamped to >= -126 so the result never goes denormal / wraps.
+__device__ __forceinline__ uint64_t ex2_emulated_pair(uint64_t x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  x = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const float kMagic = 12582912.f;  // 1.5 * 2^23: adding it with round-toward--inf leaves floor(x) in the low mantissa bits
+  const uint64_t t = f2_add_rm(x, f2_pack(kMagic, kMagic));
+  const uint64_t n = f2_add(t, f2_pack(-kMagic, -kMagic));
+  const uint64_t f = f2_sub(x, n);
+  uint64_t p = f2_fma(f, f2_pack(0.07706582f, 0.07706582f), f2_pack(0.22764632f, 0.22764632f));
+  p = f2_fma(p, f, f2_pack(0.69511649f, 0.69511649f));
+  p = f2_fma(p, f, f2_pack(1.f, 1.f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  const float r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  const float r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  return f2_pack(r0, r1);
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -112,7 +112,8 @@ int i2v_reshard_pack(const void* src, void* dst, int videos, int f_local, int se
 int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int seq_local, int channels, int world,
                        int elem_bytes, int inverse, void* stream);
 
-/* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM. */
+/* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
+ * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU). */
 int i2v_set_tuning(int key, int value);
 
 #ifdef __cplusplus

@@ -59,7 +59,7 @@ def test_dense_sdpa_large_magnitude_scores_online_softmax():
     B, H, S, d = 1, 2, 1024, 40
     q = _rand((B, S, H, d), 5) * 3
     k = _rand((B, S, H, d), 6) * torch.linspace(0.2, 4.0, S).view(1, S, 1, 1).to(torch.bfloat16)
-    v = _rand((B, S, H, d), 7)
+    v = _rand((B, S, H, d), 7) * 0.25  # near one-hot softmax: |o| ~ |v|; keep bf16 output quantisation below the tolerance
     o = ops.sdpa(*_cuda(q, k, v), 1, None, ops.MODE_FAST).float().cpu()
     assert (o - _oracle(q, k, v)).abs().max().item() <= BF16_TOL
 
