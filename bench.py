@@ -278,12 +278,16 @@ def run_b200(args, rank, world, local_rank):
         sampler.start()
     launches0 = _lib.launch_count()
     timer.enabled = True
+    if args.profiler_range:  # `ncu --profile-from-start off`: only the timed steps are captured
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         lat = one_step(args.warmup + i, lat)
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     timer.enabled = False
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -303,12 +307,13 @@ def run_b200(args, rank, world, local_rank):
                            din["image"])
         out_host.copy_(new, non_blocking=True)
 
-    for i in range(min(args.warmup, 2)):
+    e2e_steps = 0 if args.no_e2e else args.steps
+    for i in range(min(args.warmup, 2) if e2e_steps else 0):
         e2e_step(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(args.steps):
+    for i in range(e2e_steps):
         e2e_step(i)
     f1.record()
     barrier()
@@ -321,7 +326,7 @@ def run_b200(args, rank, world, local_rank):
         return
     peaks = _peaks()
     value = world * args.steps / (ms_total / 1e3)
-    e2e_value = world * args.steps / (e2e_ms_total / 1e3)
+    e2e_value = world * args.steps / (e2e_ms_total / 1e3) if e2e_steps else None
     dom = timer.summary()
     roofline = None
     if dom is not None:
@@ -357,6 +362,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="developer runs under a profiler: skip the host-buffer leg")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

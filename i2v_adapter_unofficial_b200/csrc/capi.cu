@@ -149,7 +149,8 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
   int rc = get_encode_fn();
   if (rc) return rc;
   const int dk = dense_dk(d);
-  const int bn = dense_block_n(dk);
+  const int variant = g_tuning[3];
+  const int bn = (dk == 48 && variant == 1 && seg_split < 0) ? 64 : dense_block_n(dk);
   if (seg_split >= 0 && skv > bn)
     return fail(I2V_ERR_UNSUPPORTED, "two-segment softmax needs skv (%d) <= %d", skv, bn);
   i2v::DenseParams P;
@@ -179,6 +180,14 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
     case 16:  return launch_dense_cfg<i2v::DenseCfg<16, 128, 4>>(P, stream);
     case 32:  return launch_dense_cfg<i2v::DenseCfg<32, 128, 4>>(P, stream);
     case 48:
+      if (bn == 64) {
+        switch (emu) {
+          case 0:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 0, 2>>(P, stream);
+          case 2:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 2, 2>>(P, stream);
+          case 4:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 4, 2>>(P, stream);
+          default: return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 3, 2>>(P, stream);
+        }
+      }
       switch (emu) {
         case 0:  return launch_dense_cfg<i2v::DenseCfg<48, 128, 4, 0>>(P, stream);
         case 2:  return launch_dense_cfg<i2v::DenseCfg<48, 128, 4, 2>>(P, stream);

@@ -42,9 +42,10 @@ struct DenseParams {
 // EMU_ = how many of every 8 (key, key+1) pairs get their 2^x from the FMA-pipe polynomial instead of MUFU.EX2.
 // At d = 40 the kernel is exp-bound (16384 exps per 128x128 tile at 16 MUFU/clk/SM = 1024 clk against 384 clk of
 // MMA), so part of the exponentials is moved to the otherwise idle FMA pipe.
-template <int DK_, int BLOCK_N_, int NSTAGES_, int EMU_ = 0>
+template <int DK_, int BLOCK_N_, int NSTAGES_, int EMU_ = 0, int MIN_CTAS_ = 1>
 struct DenseCfg {
   static constexpr int EMU = EMU_;
+  static constexpr int MIN_CTAS = MIN_CTAS_;  // co-resident CTAs per SM the register / TMEM budget is sized for
   static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16 (MMA K of QK^T, N of PV)
   static constexpr int BLOCK_N = BLOCK_N_;  // keys per tile
   static constexpr int NSTAGES = NSTAGES_;
@@ -58,17 +59,20 @@ struct DenseCfg {
   static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_S0 = 0, TMEM_S1 = BLOCK_N, TMEM_O0 = 2 * BLOCK_N, TMEM_O1 = 2 * BLOCK_N + DK;
   static constexpr int TMEM_COLS_USED = 2 * BLOCK_N + 2 * DK;
+  static constexpr int TMEM_ALLOC = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
+                                    : TMEM_COLS_USED <= 256 ? 256 : 512;
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
+  static_assert(TMEM_ALLOC * MIN_CTAS <= 512, "TMEM budget across co-resident CTAs");
   static_assert(DK % 16 == 0 && DK >= 16 && DK <= 256, "DK");
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 128, "BLOCK_N");
-  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+  static_assert(SMEM_BYTES * MIN_CTAS <= 227 * 1024, "smem budget");
 };
 
 constexpr int kDenseThreads = 320;
 constexpr float kRescaleThreshold = 8.0f;  // lazy O rescale: only when the running max grows by > 2^8
 
 template <class Cfg>
-__global__ void __launch_bounds__(kDenseThreads, 1) dense_attn_kernel(const __grid_constant__ DenseParams P) {
+__global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kernel(const __grid_constant__ DenseParams P) {
   constexpr int DK = Cfg::DK, BN = Cfg::BLOCK_N, NS = Cfg::NSTAGES, KSUB = Cfg::KSUB, KSTEPS = Cfg::KSTEPS;
 
   extern __shared__ uint8_t smem_raw[];
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_attn_kernel(const __gr
     mbar_fence_init();
   }
   if (warp == 9) {
-    tmem_alloc<512>(tmem_base_slot);
+    tmem_alloc<Cfg::TMEM_ALLOC>(tmem_base_slot);
   }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&prob.tm_q);
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) dense_attn_kernel(const __gr
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_ALLOC>(tmem_base);
   }
 }
 

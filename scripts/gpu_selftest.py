@@ -205,7 +205,66 @@ def group_perf():
     return True
 
 
-GROUPS = {"generic": group_generic, "temporal": group_temporal, "dense64": group_dense64, "dense": group_dense,
+def group_perfdense():
+    """A few launches of the level-0 fused self + cross-frame kernel (C2 shape) for ncu captures."""
+    import torch
+    from i2v_adapter_unofficial_b200 import ops
+
+    torch.manual_seed(3)
+    Bv, Fr, H, S, d = 2, 16, 8, 4096, 40
+    y = torch.randn(Bv * Fr, S, 4, H, d, device="cuda", dtype=torch.bfloat16)
+    kvx = torch.randn(Bv, S, 2, H, d, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.fused_self_xframe(y[:, :, 0], y[:, :, 1], y[:, :, 2], y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1], Fr,
+                                       None, ops.MODE_FAST)
+    ms = _time(fn, iters=3, warm=2)
+    fl = 2 * 4.0 * Bv * Fr * H * S * S * d
+    print(f"[perf] fused self+xframe L0 (C2): {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    return True
+
+
+def group_tunedense():
+    """Variant sweep of the level-0 fused kernel: tuning key 3 (tile variant) x key 2 (exp2 split)."""
+    import torch
+    from i2v_adapter_unofficial_b200 import _lib, ops
+
+    torch.manual_seed(3)
+    Bv, Fr, H, S, d = 2, 16, 8, 4096, 40
+    y = torch.randn(Bv * Fr, S, 4, H, d, device="cuda", dtype=torch.bfloat16)
+    kvx = torch.randn(Bv, S, 2, H, d, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.fused_self_xframe(y[:, :, 0], y[:, :, 1], y[:, :, 2], y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1], Fr,
+                                       None, ops.MODE_FAST)
+    fl = 2 * 4.0 * Bv * Fr * H * S * S * d
+    ref_self = ref_sdpa(y[:2, :, 0], y[:2, :, 1], y[:2, :, 2])
+    lib = _lib.load()
+    variants = [int(a) for a in os.environ.get("I2V_VARIANTS", "0,1").split(",")]
+    for variant in variants:
+        for emu in [int(a) for a in os.environ.get("I2V_EMUS", "0,1,3,4,5").split(",")]:
+            lib.i2v_set_tuning(3, variant)
+            lib.i2v_set_tuning(2, emu)
+            ms = _time(fn, iters=5, warm=2)
+            o = fn()
+            err = (o[:2, :, 0].float() - ref_self).abs().max().item()
+            print(f"[tune] variant {variant} emu-key {emu}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s  max_abs_err {err:.2e}",
+                  flush=True)
+    lib.i2v_set_tuning(3, 0)
+    lib.i2v_set_tuning(2, 0)
+    return True
+
+
+def group_perftemporal():
+    import torch
+    from i2v_adapter_unofficial_b200 import ops
+
+    torch.manual_seed(5)
+    N, Fr, H, d = 8192, 16, 8, 40
+    qkv = torch.randn(N, Fr, 3, H, d, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.temporal_attn(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], None, ops.MODE_FAST)
+    ms = _time(fn, iters=3, warm=2)
+    print(f"[perf] temporal L0 (C2): {ms * 1e3:.1f} us = {4.0 * N * Fr * H * d * 2 / ms / 1e6:.0f} GB/s", flush=True)
+    return True
+
+
+GROUPS = {"tunedense": group_tunedense, "perfdense": group_perfdense, "perftemporal": group_perftemporal, "generic": group_generic, "temporal": group_temporal, "dense64": group_dense64, "dense": group_dense,
           "fused": group_fused, "ip": group_ip, "perf": group_perf}
 
 

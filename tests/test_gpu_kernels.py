@@ -158,7 +158,7 @@ def test_fp32_check_mode(case):
 
 
 def test_auto_mode_covers_shapes_outside_the_fast_kernels():
-    q, k, v = _rand((2, 50, 3, 24), 1), _rand((2, 60, 3, 24), 2), _rand((2, 60, 3, 24), 3)   # d = 24: no tcgen05 config
+    q, k, v = _rand((2, 50, 3, 20), 1), _rand((2, 60, 3, 20), 2), _rand((2, 60, 3, 20), 3)   # d = 20: not a multiple of 8, no tcgen05 config
     with pytest.raises(_lib.I2VLibraryError) as e:
         ops.sdpa(*_cuda(q, k, v), 1, None, ops.MODE_FAST)
     assert e.value.code == -2
