@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libi2v_attn_b200.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+LIB_PATH = os.environ.get("I2V_ATTN_LIB", os.path.join(_HERE, LIB_NAME))  # env override: developer A/B builds
 
 I2V_BF16, I2V_F32 = 0, 1
 MODE_AUTO, MODE_FAST, MODE_GENERIC = 0, 1, 2

@@ -17,6 +17,10 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef I2V_TRACE
+unsigned long long* g_trace = nullptr;
+int g_trace_cta = 0;
+#endif
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -127,7 +131,7 @@ int dense_block_n(int dk) { return dk > 128 ? 64 : 128; }
 bool dense_supported(int d, int dtype) { return dtype == I2V_BF16 && d % 8 == 0 && dense_dk(d) != 0; }
 
 template <class Cfg>
-int launch_dense_cfg(const i2v::DenseParams& P, cudaStream_t stream) {
+int launch_dense_cfg(const i2v::DenseParams& Pin, cudaStream_t stream) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -136,9 +140,11 @@ int launch_dense_cfg(const i2v::DenseParams& P, cudaStream_t stream) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[dev & 63] = true;
   }
+  i2v::DenseParams P = Pin;
+  P.q_blocks = (P.sq + 128 * Cfg::NT - 1) / (128 * Cfg::NT);
   const long long grid = (long long)P.q_blocks * P.heads * P.batch * P.nprob;
   if (grid <= 0 || grid > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "dense attention grid %lld out of range", grid);
-  kern<<<(unsigned)grid, i2v::kDenseThreads, Cfg::SMEM_BYTES, stream>>>(P);
+  kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
@@ -149,18 +155,23 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
   int rc = get_encode_fn();
   if (rc) return rc;
   const int dk = dense_dk(d);
-  const int variant = g_tuning[3];
-  const int bn = (dk == 48 && variant == 1 && seg_split < 0) ? 64 : dense_block_n(dk);
+  // tile variant for d <= 48 (tuning key 3, value - 1): 0 = two 128x128 tiles, one CTA per SM; 1 (default) = two 128x64
+  // tiles per CTA, two CTAs per SM; 2 = four 128x64 tiles per CTA, each warpgroup alternating between two
+  const int variant = g_tuning[3] > 0 ? g_tuning[3] - 1 : 1;
+  const int bn = (dk == 48 && variant >= 1 && seg_split < 0) ? 64 : dense_block_n(dk);
   if (seg_split >= 0 && skv > bn)
     return fail(I2V_ERR_UNSUPPORTED, "two-segment softmax needs skv (%d) <= %d", skv, bn);
   i2v::DenseParams P;
   memset(&P, 0, sizeof(P));
   P.nprob = nseg;
   P.batch = batch; P.heads = heads; P.sq = sq; P.skv = skv; P.d = d;
-  P.q_blocks = (sq + 255) / 256;
   P.scale_log2e = scale * 1.4426950408889634f;
   P.seg_split = seg_split;
   P.seg_scale = seg_scale;
+#ifdef I2V_TRACE
+  P.trace = g_trace;
+  P.trace_cta = g_trace_cta;
+#endif
   for (int i = 0; i < nseg; ++i) {
     const DenseSeg& s = segs[i];
     if (batch % s.kv_group) return fail(I2V_ERR_BAD_SHAPE, "batch %d not divisible by kv_group %d", batch, s.kv_group);
@@ -180,12 +191,20 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
     case 16:  return launch_dense_cfg<i2v::DenseCfg<16, 128, 4>>(P, stream);
     case 32:  return launch_dense_cfg<i2v::DenseCfg<32, 128, 4>>(P, stream);
     case 48:
+      if (bn == 64 && variant == 2) {  // four query tiles per CTA, each warpgroup alternates between two
+        switch (emu) {
+          case 0:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 0, 1, 2>>(P, stream);
+          case 2:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 2, 1, 2>>(P, stream);
+          case 4:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 4, 1, 2>>(P, stream);
+          default: return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 3, 1, 2>>(P, stream);
+        }
+      }
       if (bn == 64) {
         switch (emu) {
-          case 0:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 0, 2>>(P, stream);
-          case 2:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 2, 2>>(P, stream);
-          case 4:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 4, 2>>(P, stream);
-          default: return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 3, 2>>(P, stream);
+          case 0:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 0, 2, 1, 1>>(P, stream);
+          case 3:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 3, 2, 1, 1>>(P, stream);
+          case 4:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 4, 2, 1, 1>>(P, stream);
+          default: return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 2, 2, 1, 1>>(P, stream);
         }
       }
       switch (emu) {
@@ -314,6 +333,15 @@ int i2v_device_supported(void) {
   DeviceInfo* di = nullptr;
   return device_info(&di) == 0 ? 1 : 0;
 }
+
+#ifdef I2V_TRACE
+// developer builds only (not part of the C ABI): device buffer of 16 * 1024 uint64 for the dense-kernel timeline
+int i2v_debug_set_trace(void* device_buffer, int cta) {
+  g_trace = (unsigned long long*)device_buffer;
+  g_trace_cta = cta;
+  return 0;
+}
+#endif
 
 int i2v_set_tuning(int key, int value) {
   if (key < 0 || key >= 8) return fail(I2V_ERR_BAD_SHAPE, "unknown tuning key %d", key);

@@ -9,13 +9,30 @@
 //     src/models/unet_motion_cross_frame_attn.py:1264-1279): one KV tile holding [text | image] tokens with a
 //     two-segment softmax (seg_split) and the image branch scaled by seg_scale.
 //
-// CTA = 320 threads:  warps 0-3 softmax/epilogue for query tile A (rows q0 .. q0+127)
-//                     warps 4-7 softmax/epilogue for query tile B (rows q0+128 .. q0+255)
-//                     warp 8    TMA producer,  warp 9  MMA issuer (+ TMEM allocation)
-// TMEM columns:       [0,BN) S_A / P_A   [BN,2BN) S_B / P_B   [2BN,2BN+DK) O_A   [2BN+DK,2BN+2DK) O_B
+// CTA:  warps 0-3 softmax/epilogue warpgroup 0, warps 4-7 softmax/epilogue warpgroup 1, warp 8 TMA producer,
+//       warps 9 .. 9+NMW-1 MMA issuers (warp 9 also owns the TMEM allocation).
+// A CTA owns NT = 2*TPW query tiles of 128 rows; tile i belongs to warpgroup i % 2.  With TPW = 2 a warpgroup
+// alternates between its two tiles, so the QK^T / PV MMAs of one tile run while the warpgroup does the softmax of
+// the other one and the softmax warps never idle on the tensor pipe round trip (at d = 40 the kernel is bound by
+// the exponentials, not by the MMAs).
+// TMEM columns:       [i*BN, (i+1)*BN) S_i / P_i (bf16 P aliases the fp32 scores)   [NT*BN + i*DK, +DK) O_i
 #pragma once
 #include <cuda.h>
 #include "ptx_sm100.cuh"
+
+// Developer timeline trace (-DI2V_TRACE): one CTA records clock64() at phase boundaries of one softmax warp per
+// warpgroup and of the MMA warps into a global buffer, [warp slot][event] = (tag << 48) | (clock & 0xffffffffffff).
+#ifdef I2V_TRACE
+#define I2V_TRACE_DECL unsigned long long* tr_ptr = nullptr; int tr_n = 0;
+#define I2V_TRACE_INIT(slot)                                                                         \
+  if (P.trace != nullptr && blockIdx.x == P.trace_cta && lane == 0) tr_ptr = P.trace + (slot) * 1024;
+#define I2V_TRACE_EV(tag)                                                                            \
+  if (tr_ptr != nullptr && tr_n < 1024) tr_ptr[tr_n++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xffffffffffffull);
+#else
+#define I2V_TRACE_DECL
+#define I2V_TRACE_INIT(slot)
+#define I2V_TRACE_EV(tag)
+#endif
 
 namespace i2v {
 
@@ -33,17 +50,23 @@ struct DenseParams {
   DenseProblem prob[2];
   int nprob;
   int batch, heads, sq, skv, d;
-  int q_blocks;        // ceil(sq / 256)
+  int q_blocks;        // ceil(sq / (128 * Cfg::NT))
   float scale_log2e;   // softmax scale * log2(e)
   int seg_split;       // <0: plain softmax. >=0: two-segment softmax (single KV tile), columns >= seg_split
   float seg_scale;     //      form the second segment whose normalised probabilities are multiplied by seg_scale
+  unsigned long long* trace;  // developer timeline trace buffer (only read by -DI2V_TRACE builds), else null
+  int trace_cta;
 };
 
 // EMU_ = how many of every 8 (key, key+1) pairs get their 2^x from the FMA-pipe polynomial instead of MUFU.EX2.
 // At d = 40 the kernel is exp-bound (16384 exps per 128x128 tile at 16 MUFU/clk/SM = 1024 clk against 384 clk of
 // MMA), so part of the exponentials is moved to the otherwise idle FMA pipe.
-template <int DK_, int BLOCK_N_, int NSTAGES_, int EMU_ = 0, int MIN_CTAS_ = 1>
+template <int DK_, int BLOCK_N_, int NSTAGES_, int EMU_ = 0, int MIN_CTAS_ = 1, int TPW_ = 1, int NMW_ = 0>
 struct DenseCfg {
+  static constexpr int TPW = TPW_;      // query tiles per softmax warpgroup
+  static constexpr int NT = 2 * TPW_;   // query tiles per CTA
+  static constexpr int NMW = NMW_ > 0 ? NMW_ : NT;  // MMA-issuing warps (tile t is issued by warp t % NMW)
+  static constexpr int THREADS = (9 + NMW) * 32;
   static constexpr int EMU = EMU_;
   static constexpr int MIN_CTAS = MIN_CTAS_;  // co-resident CTAs per SM the register / TMEM budget is sized for
   static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16 (MMA K of QK^T, N of PV)
@@ -56,9 +79,9 @@ struct DenseCfg {
   static constexpr int Q_TILE_BYTES = KSUB * Q_SUB_BYTES;
   static constexpr int KV_TILE_BYTES = KSUB * KV_SUB_BYTES;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = 2 * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_S0 = 0, TMEM_S1 = BLOCK_N, TMEM_O0 = 2 * BLOCK_N, TMEM_O1 = 2 * BLOCK_N + DK;
-  static constexpr int TMEM_COLS_USED = 2 * BLOCK_N + 2 * DK;
+  static constexpr int SMEM_BYTES = NT * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_S0 = 0, TMEM_O0 = NT * BLOCK_N;  // tile i: S at TMEM_S0 + i*BLOCK_N, O at TMEM_O0 + i*DK
+  static constexpr int TMEM_COLS_USED = NT * (BLOCK_N + DK);
   static constexpr int TMEM_ALLOC = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
                                     : TMEM_COLS_USED <= 256 ? 256 : 512;
   static_assert(TMEM_COLS_USED <= 512, "TMEM budget");
@@ -68,27 +91,28 @@ struct DenseCfg {
   static_assert(SMEM_BYTES * MIN_CTAS <= 227 * 1024, "smem budget");
 };
 
-constexpr int kDenseThreads = 320;
 constexpr float kRescaleThreshold = 8.0f;  // lazy O rescale: only when the running max grows by > 2^8
 
 template <class Cfg>
-__global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kernel(const __grid_constant__ DenseParams P) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dense_attn_kernel(const __grid_constant__ DenseParams P) {
   constexpr int DK = Cfg::DK, BN = Cfg::BLOCK_N, NS = Cfg::NSTAGES, KSUB = Cfg::KSUB, KSTEPS = Cfg::KSTEPS;
+  constexpr int NT = Cfg::NT, TPW = Cfg::TPW;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sm_q = smem;                                  // [2][KSUB][128 rows][128 B]
-  uint8_t* sm_k = sm_q + 2 * Cfg::Q_TILE_BYTES;          // [NS][KSUB][BN rows][128 B]
+  uint8_t* sm_q = smem;                                  // [NT][KSUB][128 rows][128 B]
+  uint8_t* sm_k = sm_q + NT * Cfg::Q_TILE_BYTES;         // [NS][KSUB][BN rows][128 B]
   uint8_t* sm_v = sm_k + NS * Cfg::KV_TILE_BYTES;        // [NS][KSUB][BN rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + NS * Cfg::KV_TILE_BYTES);
   uint64_t* bar_q_full = bars + 0;      // [1]
   uint64_t* bar_k_full = bars + 1;      // [NS]
   uint64_t* bar_v_full = bars + 1 + NS; // [NS]
   uint64_t* bar_kv_empty = bars + 1 + 2 * NS;  // [NS]
-  uint64_t* bar_s_full = bars + 1 + 3 * NS;    // [2]
-  uint64_t* bar_p_full = bars + 3 + 3 * NS;    // [2]
-  uint64_t* bar_o_full = bars + 5 + 3 * NS;    // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 7 + 3 * NS);
+  uint64_t* bar_s_full = bars + 1 + 3 * NS;            // [NT]
+  uint64_t* bar_p_full = bars + 1 + 3 * NS + NT;       // [NT]
+  uint64_t* bar_o_full = bars + 1 + 3 * NS + 2 * NT;   // [NT]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 1 + 3 * NS + 3 * NT);
+  static_assert((2 + 3 * NS + 3 * NT) * 8 <= Cfg::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,9 +124,8 @@ __global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kerne
   const int b = x % P.batch;      x /= P.batch;
   const int pi = x;  // problem index
   const DenseProblem& prob = P.prob[pi];
-  const int q0 = qb * 256;
-  const bool tile_b_active = (q0 + 128) < P.sq;
-  const int ntiles = tile_b_active ? 2 : 1;
+  const int q0 = qb * (128 * NT);
+  const int ntiles = min(NT, (P.sq - q0 + 127) / 128);  // active query tiles of this CTA
   const int n_kv = (P.skv + BN - 1) / BN;
   const int bkv = b / prob.kv_group;
 
@@ -111,9 +134,9 @@ __global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kerne
     for (int s = 0; s < NS; ++s) {
       mbar_init(bar_k_full + s, 1);
       mbar_init(bar_v_full + s, 1);
-      mbar_init(bar_kv_empty + s, 1);
+      mbar_init(bar_kv_empty + s, min(Cfg::NMW, ntiles));  // one commit per MMA warp that owns a tile
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NT; ++t) {
       mbar_init(bar_s_full + t, 1);
       mbar_init(bar_p_full + t, 128);
       mbar_init(bar_o_full + t, 1);
@@ -155,82 +178,111 @@ __global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kerne
                       j * BN, bkv, kEvictLast);
       }
     }
-  } else if (warp == 9) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+  } else if (warp >= 9) {
+    // =========================== MMA issuers ===========================
+    // NMW warps; warp w owns query tiles w, w + NMW, ...  All 32 lanes wait on the barriers, one elected lane issues
+    // (the elect.sync form keeps the tcgen05 operands in uniform registers; a divergent `lane == 0` region makes
+    // the compiler wrap every UTCHMMA in a serialising loop and turns the issuing thread into the bottleneck).
+    const int mw = warp - 9;
+    I2V_TRACE_DECL
+    I2V_TRACE_INIT(8 + mw)
+    if (mw < ntiles) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, DK, 0, 1);
       const uint32_t q_addr = smem_u32(sm_q);
       const uint32_t k_addr = smem_u32(sm_k);
       const uint32_t v_addr = smem_u32(sm_v);
-      const uint32_t tm_s[2] = {tmem_base + Cfg::TMEM_S0, tmem_base + Cfg::TMEM_S1};
-      const uint32_t tm_o[2] = {tmem_base + Cfg::TMEM_O0, tmem_base + Cfg::TMEM_O1};
+      // descriptor templates: everything except the 14-bit start-address field is constant
+      const uint64_t desc_k_major = make_smem_desc_sw128(0, 16, 1024);
+      const uint64_t desc_v = make_smem_desc_sw128(0, Cfg::KV_SUB_BYTES, 1024);
 
       auto issue_qk = [&](int t, int s) {
-        const uint32_t qa = q_addr + t * Cfg::Q_TILE_BYTES;
-        const uint32_t ka = k_addr + s * Cfg::KV_TILE_BYTES;
+        const uint32_t qa = (q_addr + t * Cfg::Q_TILE_BYTES) >> 4;
+        const uint32_t ka = (k_addr + s * Cfg::KV_TILE_BYTES) >> 4;
+        const uint32_t ds = tmem_base + Cfg::TMEM_S0 + t * BN;
 #pragma unroll
         for (int kk = 0; kk < KSTEPS; ++kk) {
           const uint32_t sub = kk >> 2, off = (kk & 3) * 32;
-          const uint64_t da = make_smem_desc_sw128(qa + sub * Cfg::Q_SUB_BYTES + off, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(ka + sub * Cfg::KV_SUB_BYTES + off, 16, 1024);
-          umma_ss(tm_s[t], da, db, idesc_qk, kk > 0 ? 1u : 0u);
+          const uint64_t da = desc_k_major | (uint64_t)((qa + ((sub * Cfg::Q_SUB_BYTES + off) >> 4)) & 0x3FFF);
+          const uint64_t db = desc_k_major | (uint64_t)((ka + ((sub * Cfg::KV_SUB_BYTES + off) >> 4)) & 0x3FFF);
+          umma_ss(ds, da, db, idesc_qk, kk > 0 ? 1u : 0u);
         }
       };
       auto issue_pv = [&](int t, int s, bool accumulate) {
-        const uint32_t va = v_addr + s * Cfg::KV_TILE_BYTES;
+        const uint32_t va = (v_addr + s * Cfg::KV_TILE_BYTES) >> 4;
+        const uint32_t ds = tmem_base + Cfg::TMEM_S0 + t * BN;
+        const uint32_t dout = tmem_base + Cfg::TMEM_O0 + t * DK;
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk) {
           // B = V tile, MN-major: 16 key rows per k-step (2048 B), 64-column atoms KV_SUB_BYTES apart.
-          const uint64_t db = make_smem_desc_sw128(va + kk * 2048, Cfg::KV_SUB_BYTES, 1024);
-          umma_ts(tm_o[t], tm_s[t] + kk * 8, db, idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
+          const uint64_t db = desc_v | (uint64_t)((va + kk * (2048 >> 4)) & 0x3FFF);
+          umma_ts(dout, ds + kk * 8, db, idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
         }
       };
 
       mbar_wait(bar_q_full, 0);
       mbar_wait(bar_k_full + 0, 0);
       tc_fence_after();
-      for (int t = 0; t < ntiles; ++t) {
-        issue_qk(t, 0);
-        tc_commit(bar_s_full + t);
+      if (elect_one()) {
+        for (int t = mw; t < ntiles; t += Cfg::NMW) {
+          issue_qk(t, 0);
+          tc_commit(bar_s_full + t);
+        }
       }
+      __syncwarp();
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % NS;
         const uint32_t ph = (j / NS) & 1;
         const int sn = (j + 1) % NS;
         const uint32_t phn = ((j + 1) / NS) & 1;
+        const bool more = j + 1 < n_kv;
         mbar_wait(bar_v_full + s, ph);
-        if (j + 1 < n_kv) mbar_wait(bar_k_full + sn, phn);
-        for (int t = 0; t < ntiles; ++t) {
+        if (more) mbar_wait(bar_k_full + sn, phn);
+        for (int t = mw; t < ntiles; t += Cfg::NMW) {
+          I2V_TRACE_EV(0x100 + t)
           mbar_wait(bar_p_full + t, j & 1);
           tc_fence_after();
-          issue_pv(t, s, j > 0);
-          if (j + 1 < n_kv) {
-            issue_qk(t, sn);
-            tc_commit(bar_s_full + t);
-          } else {
-            tc_commit(bar_o_full + t);
+          I2V_TRACE_EV(0x110 + t)
+          if (elect_one()) {
+            issue_pv(t, s, j > 0);
+            if (more) {
+              issue_qk(t, sn);
+              tc_commit(bar_s_full + t);
+            } else {
+              tc_commit(bar_o_full + t);
+            }
           }
+          __syncwarp();
+          I2V_TRACE_EV(0x120 + t)
         }
-        tc_commit(bar_kv_empty + s);
+        if (elect_one()) tc_commit(bar_kv_empty + s);
+        __syncwarp();
       }
     }
   } else {
     // =========================== softmax + epilogue warpgroups ===========================
-    const int t = warp >> 2;             // query tile handled by this warpgroup
-    if (t < ntiles) {
-      const int row = (warp & 3) * 32 + lane;  // TMEM lane == query row within the tile
-      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tm_s = tmem_base + (t == 0 ? Cfg::TMEM_S0 : Cfg::TMEM_S1) + lane_addr;
-      const uint32_t tm_o = tmem_base + (t == 0 ? Cfg::TMEM_O0 : Cfg::TMEM_O1) + lane_addr;
-      const float c = P.scale_log2e;
-      float m_ref = -INFINITY;  // running reference max (in the scaled log2 domain)
-      float l = 0.f;            // running row sum
-      const bool two_seg = P.seg_split >= 0;
+    const int wg = warp >> 2;                    // warpgroup 0 / 1 owns query tiles wg, wg + 2, ...
+    const int row = (warp & 3) * 32 + lane;      // TMEM lane == query row within a tile
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const float c = P.scale_log2e;
+    const bool two_seg = P.seg_split >= 0;
+    I2V_TRACE_DECL
+    if ((warp & 3) == 0) { I2V_TRACE_INIT(wg) }
+    float m_ref[TPW], l[TPW];  // per tile: running reference max (scaled log2 domain) and running row sum
+#pragma unroll
+    for (int tt = 0; tt < TPW; ++tt) { m_ref[tt] = -INFINITY; l[tt] = 0.f; }
 
-      for (int j = 0; j < n_kv; ++j) {
+    for (int j = 0; j < n_kv; ++j) {
+#pragma unroll
+      for (int tt = 0; tt < TPW; ++tt) {
+        const int t = tt * 2 + wg;  // query tile index within the CTA
+        if (t >= ntiles) continue;
+        const uint32_t tm_s = tmem_base + Cfg::TMEM_S0 + t * BN + lane_addr;
+        const uint32_t tm_o = tmem_base + Cfg::TMEM_O0 + t * DK + lane_addr;
+        I2V_TRACE_EV(0x10 + t)
         mbar_wait(bar_s_full + t, j & 1);
         tc_fence_after();
+        I2V_TRACE_EV(0x20 + t)
         float sv[BN];
 #pragma unroll
         for (int cch = 0; cch < BN / 32; ++cch) {
@@ -240,34 +292,49 @@ __global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kerne
           for (int i = 0; i < 32; ++i) sv[cch * 32 + i] = __uint_as_float(r[i]);
         }
         tc_wait_ld();
+        I2V_TRACE_EV(0x30 + t)
         const int valid = P.skv - j * BN;  // columns >= valid are padding
 
         if (!two_seg) {
-          if (valid < BN) {  // ragged last tile only (warp-uniform)
+          const bool full = valid >= BN;
+          if (!full) {  // ragged last tile only (warp-uniform)
 #pragma unroll
             for (int i = 0; i < BN; ++i)
               if (i >= valid) sv[i] = -INFINITY;
           }
-          // row max: 4 independent FMNMX3 chains
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          // P = 2^(c*s - mref) -> bf16 -> TMEM (aliasing S); returns the row sum.  `emu`: part of the exponentials on
+          // the FMA pipe (never for ragged tiles: their -inf padding must go through MUFU, ex2(-inf) = 0).
+          auto exp_pass = [&](float mref, bool emu) -> float {
+            const uint64_t c2 = f2_pack(c, c);
+            const uint64_t nm2 = f2_pack(-mref, -mref);
+            uint64_t ls0 = 0ull, ls1 = 0ull;  // two packed partial row sums
 #pragma unroll
-          for (int i = 0; i < BN; i += 8) {
-            mx0 = fmax3(mx0, sv[i + 0], sv[i + 1]);
-            mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
-            mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]);
-            mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
-          }
-          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
-          // lazy rescale: keep the old reference unless the max grew by more than the threshold
-          float alpha = 1.f;
-          bool need = false;
-          if (mx > m_ref + kRescaleThreshold || m_ref == -INFINITY) {
-            alpha = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - mx);
-            m_ref = mx;
-            need = true;
-          }
-          if (j > 0 && __any_sync(0xffffffffu, need)) {
-            // correct the O accumulator of this row (PV of tile j-1 has retired: s_full(j) was committed after it)
+            for (int cch = 0; cch < BN / 32; ++cch) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint64_t x = f2_fma(f2_pack(sv[cch * 32 + 2 * i], sv[cch * 32 + 2 * i + 1]), c2, nm2);
+                uint64_t p2;
+                if ((i & 7) < Cfg::EMU && emu) {
+                  p2 = ex2_emulated_pair(x);
+                } else {
+                  float x0, x1;
+                  f2_unpack(x, x0, x1);
+                  p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+                }
+                if (i & 1) ls1 = f2_add(ls1, p2); else ls0 = f2_add(ls0, p2);
+                float p0, p1;
+                f2_unpack(p2, p0, p1);
+                pk[i] = pack_bf16x2(p0, p1);
+              }
+              tmem_st_x16(tm_s + cch * 16, pk);
+            }
+            float a0, a1;
+            f2_unpack(f2_add(ls0, ls1), a0, a1);
+            return a0 + a1;
+          };
+          // multiply the O accumulator row by alpha (PV of tile j-1 has retired: s_full(j) was committed after it)
+          auto rescale_o = [&](float alpha) {
 #pragma unroll
             for (int cch = 0; cch < DK / 16; ++cch) {
               uint32_t r[16];
@@ -278,36 +345,49 @@ __global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kerne
               tmem_st_x16(tm_o + cch * 16, r);
             }
             tc_wait_st();
+          };
+          // row max: 4 independent FMNMX3 chains
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < BN; i += 8) {
+            mx0 = fmax3(mx0, sv[i + 0], sv[i + 1]);
+            mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+            mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]);
+            mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
           }
-          l *= alpha;
-          const uint64_t c2 = f2_pack(c, c);
-          const uint64_t nm2 = f2_pack(-m_ref, -m_ref);
-          uint64_t ls0 = 0ull, ls1 = 0ull;  // two packed partial row sums
-          const bool allow_emu = valid >= BN;  // -inf padding must go through MUFU (ex2(-inf) = 0)
-#pragma unroll
-          for (int cch = 0; cch < BN / 32; ++cch) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const uint64_t x = f2_fma(f2_pack(sv[cch * 32 + 2 * i], sv[cch * 32 + 2 * i + 1]), c2, nm2);
-              uint64_t p2;
-              if ((i & 7) < Cfg::EMU && allow_emu) {
-                p2 = ex2_emulated_pair(x);
-              } else {
-                float x0, x1;
-                f2_unpack(x, x0, x1);
-                p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+          float sum;
+          if (j > 0 && full) {
+            // Optimistic step: the exponentials start right away against the running reference max, the row max of
+            // this tile is computed alongside (independent instruction streams: MUFU and FMNMX3 interleave).  Only
+            // if some row's max outgrew the reference by more than the lazy-rescale threshold is the step redone.
+            sum = exp_pass(m_ref[tt], true);
+            const bool need = mx > m_ref[tt] + kRescaleThreshold;
+            if (__any_sync(0xffffffffu, need)) {
+              float alpha = 1.f;
+              if (need) {
+                alpha = ex2_approx(m_ref[tt] - mx);
+                m_ref[tt] = mx;
               }
-              if (i & 1) ls1 = f2_add(ls1, p2); else ls0 = f2_add(ls0, p2);
-              float p0, p1;
-              f2_unpack(p2, p0, p1);
-              pk[i] = pack_bf16x2(p0, p1);
+              rescale_o(alpha);
+              l[tt] *= alpha;
+              sum = exp_pass(m_ref[tt], true);
             }
-            tmem_st_x16(tm_s + cch * 16, pk);
+          } else {
+            // first tile (no reference yet) and ragged last tile: max first, then the exponentials
+            float alpha = 1.f;
+            bool need = false;
+            if (mx > m_ref[tt] + kRescaleThreshold || m_ref[tt] == -INFINITY) {
+              alpha = (m_ref[tt] == -INFINITY) ? 0.f : ex2_approx(m_ref[tt] - mx);
+              m_ref[tt] = mx;
+              need = true;
+            }
+            if (j > 0 && __any_sync(0xffffffffu, need)) rescale_o(alpha);
+            l[tt] *= alpha;
+            sum = exp_pass(m_ref[tt], full);
           }
-          float a0, a1;
-          f2_unpack(f2_add(ls0, ls1), a0, a1);
-          l += a0 + a1;
+          I2V_TRACE_EV(0x40 + t)
+          l[tt] += sum;
         } else {
           // two-segment softmax over a single KV tile: [0,split) and [split,valid); probabilities are
           // normalised here so the accumulator needs no final division.
@@ -339,17 +419,25 @@ __global__ void __launch_bounds__(kDenseThreads, Cfg::MIN_CTAS) dense_attn_kerne
             }
             tmem_st_x16(tm_s + cch * 16, pk);
           }
-          l = 1.f;
+          l[tt] = 1.f;
         }
+        I2V_TRACE_EV(0x50 + t)
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(bar_p_full + t);
+        I2V_TRACE_EV(0x60 + t)
       }
+    }
 
-      // ---- epilogue: O / l -> bf16 -> global ----
+    // ---- epilogue: O / l -> bf16 -> global ----
+#pragma unroll
+    for (int tt = 0; tt < TPW; ++tt) {
+      const int t = tt * 2 + wg;
+      if (t >= ntiles) continue;
+      const uint32_t tm_o = tmem_base + Cfg::TMEM_O0 + t * DK + lane_addr;
       mbar_wait(bar_o_full + t, 0);
       tc_fence_after();
-      const float inv_l = 1.f / l;
+      const float inv_l = 1.f / l[tt];
       const int qrow = q0 + t * 128 + row;
       __nv_bfloat16* orow = prob.o + (long long)b * prob.o_sb + (long long)qrow * prob.o_ss + (long long)h * prob.o_sh;
 #pragma unroll

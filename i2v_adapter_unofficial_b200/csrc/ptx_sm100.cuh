@@ -296,6 +296,23 @@ __device__ __forceinline__ uint64_t ex2_emulated_pair(uint64_t x) {
   return f2_pack(r0, r1);
 }
 
+// Same without the lower clamp: the caller guarantees x >= -126 (or does not care about garbage for such x).
+__device__ __forceinline__ uint64_t ex2_emulated_pair_noclamp(uint64_t x) {
+  const float kMagic = 12582912.f;
+  const uint64_t t = f2_add_rm(x, f2_pack(kMagic, kMagic));
+  const uint64_t n = f2_add(t, f2_pack(-kMagic, -kMagic));
+  const uint64_t f = f2_sub(x, n);
+  uint64_t p = f2_fma(f, f2_pack(0.07706582f, 0.07706582f), f2_pack(0.22764632f, 0.22764632f));
+  p = f2_fma(p, f, f2_pack(0.69511649f, 0.69511649f));
+  p = f2_fma(p, f, f2_pack(1.f, 1.f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  const float r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  const float r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  return f2_pack(r0, r1);
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -405,7 +405,7 @@ def apply_attn_processors(module: nn.Module, processors: Dict[str, Any]) -> None
 
 def _module_by_path(root: nn.Module, path: str) -> nn.Module:
     m = root
-    for part in path.split("."):
+    for part in (path.split(".") if path else []):
         m = getattr(m, part) if not part.isdigit() else m[int(part)]
     return m
 
@@ -432,7 +432,7 @@ def install(unet: nn.Module, mode: int = MODE_AUTO, fuse_cross_frame: bool = Tru
 
     for name, old in previous.items():
         path = name[: -len(".processor")]
-        parent_path, leaf = path.rsplit(".", 1)
+        parent_path, _, leaf = path.rpartition(".")  # parent_path == "" when `unet` is itself the transformer block
         if ".motion_modules." in f".{path}." or path.startswith("motion_modules."):
             new[name] = B200TemporalAttnProcessor(mode)
             continue

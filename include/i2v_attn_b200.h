@@ -113,7 +113,8 @@ int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int 
                        int elem_bytes, int inverse, void* stream);
 
 /* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
- * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU). */
+ * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),
+ * key 3: dense-attention tile variant + 1 for head dims <= 48 (see capi.cu). */
 int i2v_set_tuning(int key, int value);
 
 #ifdef __cplusplus

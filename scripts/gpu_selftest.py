@@ -239,7 +239,7 @@ def group_tunedense():
     variants = [int(a) for a in os.environ.get("I2V_VARIANTS", "0,1").split(",")]
     for variant in variants:
         for emu in [int(a) for a in os.environ.get("I2V_EMUS", "0,1,3,4,5").split(",")]:
-            lib.i2v_set_tuning(3, variant)
+            lib.i2v_set_tuning(3, variant + 1)
             lib.i2v_set_tuning(2, emu)
             ms = _time(fn, iters=5, warm=2)
             o = fn()

@@ -100,11 +100,19 @@ def test_unet_fp32_check_mode_matches_oracle(ip):
     unet = unet.to(DEV)
     install(unet)
     n0 = _lib.launch_count()
-    with torch.no_grad():
-        out = unet(sample.to(DEV), 37, True, ctx.to(DEV),
-                   added_cond_kwargs={"image_embeds": img.to(DEV)} if ip else None).sample.cpu()
+    # the out-of-scope PyTorch layers (cuDNN convolutions, cuBLAS linears) must not drop to TF32 in this check
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            out = unet(sample.to(DEV), 37, True, ctx.to(DEV),
+                       added_cond_kwargs={"image_embeds": img.to(DEV)} if ip else None).sample.cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     assert _lib.launch_count() > n0
-    assert (out - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    err, scale = (out - ref).abs().max().item(), ref.abs().max().item()
+    assert err <= 1e-3 * scale, f"max-abs {err:.3e} vs 1e-3 * {scale:.3e}"
 
 
 def test_unet_bf16_b200_vs_stock_processors_and_oracle():
