@@ -11,7 +11,7 @@ wrappers (also ``torch.ops.i2v_b200.*``), ``processors`` the drop-in processors,
 partitioner, ``hostmodel`` a minimal diffusers-0.25-compatible mirror of the reference's UNet classes (diffusers is
 not installable in this environment).
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, ops, partition  # noqa: F401
 from .processors import (  # noqa: F401
     B200AttnProcessor,
     B200CrossFrameAttnProcessor,
@@ -24,6 +24,7 @@ from .processors import (  # noqa: F401
 __all__ = [
     "install",
     "ops",
+    "partition",
     "B200AttnProcessor",
     "B200SpatialAttnProcessor",
     "B200CrossFrameAttnProcessor",

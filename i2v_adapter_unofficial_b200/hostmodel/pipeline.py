@@ -15,11 +15,12 @@ import torch
 @torch.no_grad()
 def denoise_step(unet, scheduler, latents, t, prompt_embeds, guidance_scale: float = 7.5,
                  condition_image_latents: Optional[torch.Tensor] = None, image_embeds: Optional[torch.Tensor] = None,
-                 cross_attention_kwargs=None):
-    """latents (B, F, 4, h, w); prompt_embeds (2B, 77, D) = [negative, positive] when guidance_scale > 1."""
+                 cross_attention_kwargs=None, impose_first_frame: bool = True):
+    """latents (B, F, 4, h, w); prompt_embeds (2B, 77, D) = [negative, positive] when guidance_scale > 1.
+    ``impose_first_frame=False`` is for frame shards that do not hold frame 0 (``partition.sharded_denoise_step``)."""
     has_condition = condition_image_latents is not None
     do_cfg = guidance_scale > 1.0
-    if has_condition:
+    if has_condition and impose_first_frame:
         latents[:, 0] = condition_image_latents
     latent_model_input = torch.cat([latents] * 2) if do_cfg else latents
     latent_model_input = scheduler.scale_model_input(latent_model_input, t)

@@ -55,6 +55,9 @@ class BlockState:
         self.enable_cross_frame = False
         self.num_frames: Optional[int] = None
         self.cross_done = False  # attn1's processor already produced self + cross-frame output
+        # frame-sharded runs (partition.FramePartitioner): frame 0 lives on another rank; the projected frame-0 K/V
+        # come from its owner through one broadcast instead of from the local rows b*F
+        self.first_frame_source = None
 
 
 class _PackedWeights:
@@ -214,7 +217,12 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
                                          (xo.bias if xo.bias is not None else 0)))
         y = F.linear(x, w_in[0], w_in[1]).view(BF, S, 4, H, d)
         first = x[0::Fr]  # frame 0 of every video: rows b*F (reference :484), no F-times repeat (:485)
-        kvx = F.linear(first, w_x[0], w_x[1]).view(BF // Fr, S, 2, H, d)
+        if st.first_frame_source is not None:  # frame shard: K/V of global frame 0 are broadcast by their owner
+            kvx = st.first_frame_source.broadcast_from_first_frame_owner(
+                lambda: F.linear(first, w_x[0], w_x[1]), (BF // Fr, S, 2 * inner), x.dtype, x.device
+            ).view(BF // Fr, S, 2, H, d)
+        else:
+            kvx = F.linear(first, w_x[0], w_x[1]).view(BF // Fr, S, 2, H, d)
         o = ops.fused_self_xframe(y[:, :, 0], y[:, :, 1], y[:, :, 2], y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1], Fr,
                                   attn.scale, self.mode)
         out = F.linear(o.view(BF, S, 2 * inner), w_out[0], w_out[1])
@@ -258,7 +266,12 @@ class B200CrossFrameAttnProcessor:
                            lambda: (torch.cat([attn.to_k.weight, attn.to_v.weight]),
                                     _cat_bias([attn.to_k.bias, attn.to_v.bias], [inner] * 2, attn.to_k.weight)))
         q = attn.to_q(x).view(B, S, H, d)
-        kv = F.linear(ctx, w[0], w[1]).view(ctx.shape[0], ctx.shape[1], 2, H, d)
+        if st is not None and st.first_frame_source is not None and group > 1:
+            kv = st.first_frame_source.broadcast_from_first_frame_owner(
+                lambda: F.linear(ctx, w[0], w[1]), (ctx.shape[0], ctx.shape[1], 2 * inner), x.dtype, x.device)
+        else:
+            kv = F.linear(ctx, w[0], w[1])
+        kv = kv.view(ctx.shape[0], ctx.shape[1], 2, H, d)
         o = ops.sdpa(q, kv[:, :, 0], kv[:, :, 1], group, attn.scale, self.mode)
         o = attn.to_out[0](o.view(B, S, inner))
         o = attn.to_out[1](o)
