@@ -30,6 +30,11 @@ EXPORTED_SYMBOLS = (
     "i2v_reshard_pack",
     "i2v_reshard_unpack",
     "i2v_set_tuning",
+    "i2v_layernorm_fwd",
+    "i2v_geglu_fwd",
+    "i2v_gn_stats",
+    "i2v_gn_apply_transpose",
+    "i2v_untranspose_residual",
 )
 
 
@@ -81,6 +86,17 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_reshard_unpack.argtypes = [p, p, i, i, i, i, i, i, i, p]
     lib.i2v_set_tuning.restype = i
     lib.i2v_set_tuning.argtypes = [i, i]
+    ll = ctypes.c_longlong
+    lib.i2v_layernorm_fwd.restype = i
+    lib.i2v_layernorm_fwd.argtypes = [p, p, p, p, p, ll, i, i, f, p]
+    lib.i2v_geglu_fwd.restype = i
+    lib.i2v_geglu_fwd.argtypes = [p, p, ll, i, p]
+    lib.i2v_gn_stats.restype = i
+    lib.i2v_gn_stats.argtypes = [p, p, i, i, i, i, p]
+    lib.i2v_gn_apply_transpose.restype = i
+    lib.i2v_gn_apply_transpose.argtypes = [p, p, p, p, p, i, i, i, i, i, f, p]
+    lib.i2v_untranspose_residual.restype = i
+    lib.i2v_untranspose_residual.argtypes = [p, p, p, i, i, i, i, p]
 
 
 def load() -> ctypes.CDLL:

@@ -10,6 +10,7 @@
 #include "../../include/i2v_attn_b200.h"
 #include "dense_attn_sm100.cuh"
 #include "generic_attn.cuh"
+#include "norm_layout.cuh"
 #include "temporal_attn.cuh"
 
 namespace {
@@ -538,6 +539,121 @@ int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int 
   if (blocks > (long long)di->sms * 16) blocks = (long long)di->sms * 16;
   reshard_unpack_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, total,
                                                                                videos, f_local, world, inner, inverse);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// normalisation / layout / epilogue kernels (norm_layout.cuh)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int i2v_layernorm_fwd(const void* x, const void* w, const void* b, const void* pe, void* y, long long rows, int C,
+                      int pe_rows, float eps, void* stream) {
+  if (rows <= 0 || C <= 0) return fail(I2V_ERR_BAD_SHAPE, "layernorm: sizes must be positive");
+  if (C % 8 || C > 2048) return fail(I2V_ERR_UNSUPPORTED, "layernorm: C (%d) must be a multiple of 8 and <= 2048", C);
+  if (pe != nullptr && pe_rows <= 0) return fail(I2V_ERR_BAD_SHAPE, "layernorm: pe_rows must be positive with pe");
+  if (!x || !w || !b || !y) return fail(I2V_ERR_BAD_SHAPE, "layernorm: null pointer");
+  if (!aligned16(x) || !aligned16(w) || !aligned16(b) || !aligned16(y) || (pe && !aligned16(pe)))
+    return fail(I2V_ERR_MISALIGNED, "layernorm: pointers must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const int nvec = C / 8;
+  const int maxv = (nvec + 31) / 32;
+  const long long blocks = (rows + 7) / 8;
+  if (blocks > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "layernorm: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint4 *xv = (const uint4*)x, *wv = (const uint4*)w, *bv = (const uint4*)b, *pv = (const uint4*)pe;
+  uint4* yv = (uint4*)y;
+  if (maxv <= 2)      i2v::layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
+  else if (maxv <= 3) i2v::layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
+  else if (maxv <= 5) i2v::layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
+  else                i2v::layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream) {
+  if (rows <= 0 || D <= 0) return fail(I2V_ERR_BAD_SHAPE, "geglu: sizes must be positive");
+  if (D % 8) return fail(I2V_ERR_UNSUPPORTED, "geglu: D (%d) must be a multiple of 8", D);
+  if (!x || !y) return fail(I2V_ERR_BAD_SHAPE, "geglu: null pointer");
+  if (!aligned16(x) || !aligned16(y)) return fail(I2V_ERR_MISALIGNED, "geglu: pointers must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const long long total = rows * (D / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)di->sms * 32) blocks = (long long)di->sms * 32;
+  i2v::geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, rows, D / 8);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+static int check_gn_shape(const char* what, int N, int C, int S, int G, int fg) {
+  if (N <= 0 || C <= 0 || S <= 0 || G <= 0 || fg <= 0) return fail(I2V_ERR_BAD_SHAPE, "%s: sizes must be positive", what);
+  if (N % fg) return fail(I2V_ERR_BAD_SHAPE, "%s: Batch size %d must be divisible by the number of frames %d.", what, N, fg);
+  if (C % G) return fail(I2V_ERR_BAD_SHAPE, "%s: C (%d) not divisible by the %d groups", what, C, G);
+  if (C % 64 || S % 8 || (C / G) % 2)
+    return fail(I2V_ERR_UNSUPPORTED, "%s: needs C %% 64 == 0, S %% 8 == 0 and an even group width (C=%d S=%d G=%d)", what, C, S, G);
+  if (N > 65535 || C / 64 > 65535) return fail(I2V_ERR_UNSUPPORTED, "%s: N or C too large for the launch grid", what);
+  return 0;
+}
+
+int i2v_gn_stats(const void* x, float* partial, int N, int C, int S, int G, void* stream) {
+  int rc = check_gn_shape("gn_stats", N, C, S, G, 1);
+  if (rc) return rc;
+  if (!x || !partial) return fail(I2V_ERR_BAD_SHAPE, "gn_stats: null pointer");
+  if (!aligned16(x)) return fail(I2V_ERR_MISALIGNED, "gn_stats: x must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  const long long slab = (long long)(C / G) * S;
+  if (slab % 8) return fail(I2V_ERR_UNSUPPORTED, "gn_stats: (C/G)*S must be a multiple of 8");
+  const long long blocks = (long long)N * G;
+  if (blocks > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "gn_stats: grid too large");
+  i2v::gn_partial_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, partial, slab / 8);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int i2v_gn_apply_transpose(const void* x, const float* partial, const void* w, const void* b, void* out, int N, int C,
+                           int S, int G, int fg, float eps, void* stream) {
+  int rc = check_gn_shape("gn_apply_transpose", N, C, S, G, fg);
+  if (rc) return rc;
+  if (!x || !partial || !w || !b || !out) return fail(I2V_ERR_BAD_SHAPE, "gn_apply_transpose: null pointer");
+  if (!aligned16(x) || !aligned16(out)) return fail(I2V_ERR_MISALIGNED, "gn_apply_transpose: x/out must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  i2v::GnApplyParams P;
+  P.x = (const __nv_bfloat16*)x; P.out = (__nv_bfloat16*)out; P.partial = partial;
+  P.w = (const __nv_bfloat16*)w; P.b = (const __nv_bfloat16*)b;
+  P.N = N; P.C = C; P.S = S; P.G = G; P.fg = fg; P.eps = eps;
+  dim3 grid((S + 63) / 64, C / 64, N);
+  i2v::gn_apply_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int i2v_untranspose_residual(const void* y, const void* res, void* out, int N, int C, int S, int fg, void* stream) {
+  int rc = check_gn_shape("untranspose_residual", N, C, S, 1, fg);
+  if (rc) return rc;
+  if (!y || !res || !out) return fail(I2V_ERR_BAD_SHAPE, "untranspose_residual: null pointer");
+  if (!aligned16(y) || !aligned16(res) || !aligned16(out))
+    return fail(I2V_ERR_MISALIGNED, "untranspose_residual: pointers must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  i2v::UntransposeParams P;
+  P.y = (const __nv_bfloat16*)y; P.res = (const __nv_bfloat16*)res; P.out = (__nv_bfloat16*)out;
+  P.N = N; P.C = C; P.S = S; P.fg = fg;
+  dim3 grid((S + 63) / 64, C / 64, N);
+  i2v::untranspose_residual_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -1,0 +1,261 @@
+"""Module-level fast path: the normalisation prologues, layout changes and residual epilogues *around* the attention
+operators, which the AttnProcessor boundary cannot reach ("the only way to absorb LN prologue +
+residual epilogue").  ``install(unet, fast_path=True)`` swaps the ``forward`` of four module types — parameters,
+state-dict keys and call signatures untouched — for versions that follow the same reference lines but run the
+bandwidth-bound steps in ``libi2v_attn_b200.so``:
+
+===============================  ===================================================  ================================
+module (reference)               replaced passes                                      kernels
+===============================  ===================================================  ================================
+I2VAdapterTransformer2DModel     GroupNorm, 1x1-conv proj_in + (BF,C,h,w)->(BF,S,C)   i2v_gn_stats,
+ src/modules/i2v_adapter.py      copy, (BF,S,C)->(BF,C,h,w) copy + proj_out +         i2v_gn_apply_transpose,
+ :214-234, :298-314              residual                                             i2v_untranspose_residual
+I2VAdapterTransformerBlock       norm1/2/3, GEGLU                                     i2v_layernorm_fwd, i2v_geglu_fwd
+ :420-565
+TransformerTemporalModel         GroupNorm over (C/G,F,h,w), both permute copies,     same three layout kernels with
+ (diffusers; Appendix A4)        residual add                                         fg = num_frames
+temporal BasicTransformerBlock   norm1/2/3 with ``+ pos_embed`` folded in, GEGLU      i2v_layernorm_fwd (pe), geglu
+===============================  ===================================================  ================================
+
+The 1x1 convolutions ``proj_in`` / ``proj_out`` of the spatial transformer are evaluated as token-major GEMMs on the
+same weights (``weight.view(out, in)``): a 1x1 convolution *is* that GEMM, and token-major output is what the blocks
+consume, so both layout copies disappear.  The attention calls still go through ``self.attn1(...)`` etc., i.e. through
+whatever processors are installed.
+
+Every fast forward checks its preconditions (CUDA, bf16, inference, supported shape, no mask / ada-norm options) and
+otherwise calls the module's original forward — the stock PyTorch GPU path of the host model, not a CPU fallback.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+
+def _fast_ok(x: torch.Tensor, module: nn.Module) -> bool:
+    return x.is_cuda and x.dtype == torch.bfloat16 and not module.training and not torch.is_grad_enabled()
+
+
+def _ln(x: torch.Tensor, norm: nn.LayerNorm, pe: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if norm.weight is None or norm.bias is None:
+        y = F.layer_norm(x, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
+        return y if pe is None else y + pe
+    return ops.layernorm(x.contiguous(), norm.weight, norm.bias, norm.eps, pe)
+
+
+def _ff(ff: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """FeedForward with GEGLU: net.0.proj (Linear dim -> 8 dim), fused GEGLU, net.2 (Linear 4 dim -> dim)."""
+    proj = ff.net[0].proj
+    h = ops.geglu(F.linear(x, proj.weight, proj.bias))
+    out = ff.net[2]
+    return F.linear(h, out.weight, out.bias)
+
+
+def _is_geglu_ff(ff: nn.Module) -> bool:
+    net = getattr(ff, "net", None)
+    return (net is not None and len(net) == 3 and type(net[0]).__name__ == "GEGLU" and isinstance(net[2], nn.Linear)
+            and getattr(net[1], "p", 0.0) == 0.0)
+
+
+class _PE:
+    """bf16 copy of the sinusoidal table rows [0, F) (cached per block; rebuilt if the buffer or F changes)."""
+
+    def __init__(self):
+        self.key = None
+        self.val = None
+
+    def get(self, pos_embed: nn.Module, frames: int, like: torch.Tensor) -> torch.Tensor:
+        pe = pos_embed.pe
+        key = (pe.data_ptr(), pe._version, frames, like.device, like.dtype)
+        if key != self.key:
+            self.val = pe[0, :frames].to(device=like.device, dtype=like.dtype).contiguous()
+            self.key = key
+        return self.val
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# transformer blocks
+# ----------------------------------------------------------------------------------------------------------------
+def _block_forward_fast(self, hidden_states, encoder_hidden_states, enable_cross_frame_attn, num_frames, kw, pe_cache):
+    """Shared body of I2VAdapterTransformerBlock.forward (src/modules/i2v_adapter.py:420-565) and the diffusers
+    BasicTransformerBlock.forward it extends (layer_norm flavour)."""
+    pe = None
+    if self.pos_embed is not None:
+        pe = pe_cache.get(self.pos_embed, hidden_states.shape[1], hidden_states)
+    norm_h = _ln(hidden_states, self.norm1, pe)                                                   # :445, :458-459
+    attn_output = self.attn1(norm_h, encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
+                             attention_mask=None, **kw)                                           # :468-473
+    if enable_cross_frame_attn:
+        batch_size = hidden_states.shape[0]
+        if num_frames is None:
+            raise ValueError("`num_frames` must be provided when `enable_cross_frame_attn` is True.")
+        if batch_size % num_frames != 0:
+            raise ValueError(f"Batch size {batch_size} must be divisible by the number of frames {num_frames}.")
+        proc = self.attn1.get_processor() if hasattr(self.attn1, "get_processor") else None
+        state = getattr(proc, "state", None)
+        if state is not None and state.cross_done:
+            state.cross_done = False          # attn1's processor already returned self + cross-frame (one launch)
+        else:
+            first = norm_h[0:batch_size:num_frames].repeat_interleave(num_frames, dim=0)          # :484-485
+            attn_output = attn_output + self.i2v_adapter(norm_h, encoder_hidden_states=first, attention_mask=None,
+                                                         **kw)                                    # :487-494
+    hidden_states = attn_output + hidden_states                                                   # :501
+    if self.attn2 is not None:
+        norm_h = _ln(hidden_states, self.norm2, pe)                                               # :514, :524-525
+        attn_output = self.attn2(norm_h, encoder_hidden_states=encoder_hidden_states, attention_mask=None, **kw)
+        hidden_states = attn_output + hidden_states                                               # :533
+    hidden_states = _ff(self.ff, _ln(hidden_states, self.norm3)) + hidden_states                  # :539-561
+    return hidden_states
+
+
+def _make_block_forward(module: nn.Module, original: Callable, is_i2v: bool):
+    pe_cache = _PE()
+
+    @functools.wraps(original)  # keeps the reference signature visible to inspect.signature (install()'s hooks bind it)
+    def forward(hidden_states, *args, **kwargs):
+        names = (("enable_cross_frame_attn", "num_frames", "attention_mask", "encoder_hidden_states",
+                  "encoder_attention_mask", "timestep", "cross_attention_kwargs", "class_labels", "added_cond_kwargs")
+                 if is_i2v else
+                 ("attention_mask", "encoder_hidden_states", "encoder_attention_mask", "timestep",
+                  "cross_attention_kwargs", "class_labels"))
+        bound: Dict[str, Any] = dict(zip(names, args))
+        bound.update(kwargs)
+        simple = (_fast_ok(hidden_states, module) and hidden_states.dim() == 3 and hidden_states.shape[-1] % 8 == 0
+                  and bound.get("attention_mask") is None and bound.get("encoder_attention_mask") is None
+                  and len(args) <= len(names) and set(kwargs) <= set(names)
+                  and isinstance(module.norm1, nn.LayerNorm) and isinstance(module.norm3, nn.LayerNorm)
+                  and _is_geglu_ff(module.ff) and getattr(module, "_chunk_size", None) is None)
+        if not simple:
+            return original(hidden_states, *args, **kwargs)
+        kw = dict(bound.get("cross_attention_kwargs") or {})
+        kw.pop("gligen", None)
+        return _block_forward_fast(module, hidden_states, bound.get("encoder_hidden_states"),
+                                   bool(bound.get("enable_cross_frame_attn", False)) if is_i2v else False,
+                                   bound.get("num_frames") if is_i2v else None, kw, pe_cache)
+
+    return forward
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# spatial transformer wrapper
+# ----------------------------------------------------------------------------------------------------------------
+def _layout_ok(x: torch.Tensor, norm: nn.GroupNorm) -> bool:
+    if x.dim() != 4 or not x.is_contiguous() or not norm.affine:
+        return False
+    _, C, h, w = x.shape
+    G = norm.num_groups
+    return C % 64 == 0 and (h * w) % 8 == 0 and C % G == 0 and (C // G) % 2 == 0 and x.shape[0] <= 65535
+
+
+def _make_transformer2d_forward(module: nn.Module, original: Callable):
+    @functools.wraps(original)
+    def forward(hidden_states, *args, **kwargs):
+        names = ("enable_cross_frame_attn", "encoder_hidden_states", "num_frames", "timestep", "added_cond_kwargs",
+                 "class_labels", "cross_attention_kwargs", "attention_mask", "encoder_attention_mask", "return_dict")
+        bound: Dict[str, Any] = dict(zip(names, args))
+        bound.update(kwargs)
+        conv_proj = isinstance(module.proj_in, nn.Conv2d) and module.proj_in.kernel_size == (1, 1)
+        lin_proj = isinstance(module.proj_in, nn.Linear)
+        simple = (_fast_ok(hidden_states, module) and _layout_ok(hidden_states, module.norm)
+                  and bound.get("attention_mask") is None and bound.get("encoder_attention_mask") is None
+                  and len(args) <= len(names) and set(kwargs) <= set(names) and (conv_proj or lin_proj)
+                  and module.proj_out.weight.shape[0] == hidden_states.shape[1])
+        if not simple:
+            return original(hidden_states, *args, **kwargs)
+        N, C, h, w = hidden_states.shape
+        norm = module.norm
+        # :218-234  GroupNorm(32, eps 1e-6) -> proj_in -> (BF, S, inner), without the NCHW intermediate
+        tokens = ops.group_norm_tokens(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, 1)
+        inner = module.proj_in.weight.shape[0]
+        tokens = F.linear(tokens, module.proj_in.weight.view(inner, C), module.proj_in.bias)
+        for block in module.transformer_blocks:                                                  # :244-296
+            tokens = block(tokens, enable_cross_frame_attn=bound.get("enable_cross_frame_attn", False),
+                           num_frames=bound.get("num_frames"), attention_mask=None,
+                           encoder_hidden_states=bound.get("encoder_hidden_states"), encoder_attention_mask=None,
+                           timestep=bound.get("timestep"), cross_attention_kwargs=bound.get("cross_attention_kwargs"),
+                           class_labels=bound.get("class_labels"))
+        # :298-314  proj_out -> (BF, C, h, w) -> + residual
+        tokens = F.linear(tokens, module.proj_out.weight.view(C, inner), module.proj_out.bias)
+        output = ops.tokens_to_nchw_residual(tokens.contiguous(), hidden_states, 1)
+        if not bound.get("return_dict", True):
+            return (output,)
+        return _Sample(output)
+
+    return forward
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# motion module
+# ----------------------------------------------------------------------------------------------------------------
+def _make_temporal_forward(module: nn.Module, original: Callable):
+    @functools.wraps(original)
+    def forward(hidden_states, encoder_hidden_states=None, timestep=None, class_labels=None, num_frames: int = 1,
+                cross_attention_kwargs=None, return_dict: bool = True):
+        simple = (_fast_ok(hidden_states, module) and _layout_ok(hidden_states, module.norm)
+                  and hidden_states.shape[0] % max(num_frames, 1) == 0 and isinstance(module.proj_in, nn.Linear))
+        if not simple:
+            return original(hidden_states, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
+                            class_labels=class_labels, num_frames=num_frames,
+                            cross_attention_kwargs=cross_attention_kwargs, return_dict=return_dict)
+        norm = module.norm
+        # GroupNorm over (C/G, F, h, w) per video, then (BF, C, h, w) -> (B*S, F, C) in the same pass
+        x = ops.group_norm_tokens(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, num_frames)
+        x = module.proj_in(x)
+        for block in module.transformer_blocks:
+            x = block(x, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
+                      cross_attention_kwargs=cross_attention_kwargs, class_labels=class_labels)
+        x = module.proj_out(x)
+        output = ops.tokens_to_nchw_residual(x.contiguous(), hidden_states, num_frames)
+        if not return_dict:
+            return (output,)
+        return _Sample(output)
+
+    return forward
+
+
+class _Sample:
+    """``.sample`` attribute and tuple-style ``[0]`` (what the call sites use, e.g. unet_motion_cross_frame_attn.py:326)."""
+
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, idx):
+        return (self.sample,)[idx]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# installation
+# ----------------------------------------------------------------------------------------------------------------
+def install_fast_forwards(root: nn.Module) -> List[Callable[[], None]]:
+    """Swap the forwards of every supported module under ``root``; returns the undo callbacks."""
+    undo: List[Callable[[], None]] = []
+
+    def patch(module: nn.Module, new_forward: Callable):
+        had_own = "forward" in module.__dict__
+        previous = module.__dict__.get("forward")
+        module.forward = new_forward
+
+        def restore(m=module, had=had_own, prev=previous):
+            if had:
+                m.forward = prev
+            else:
+                m.__dict__.pop("forward", None)
+
+        undo.append(restore)
+
+    for module in list(root.modules()):
+        name = type(module).__name__
+        if name == "I2VAdapterTransformerBlock":
+            patch(module, _make_block_forward(module, module.forward, True))
+        elif name == "BasicTransformerBlock":
+            patch(module, _make_block_forward(module, module.forward, False))
+        elif name == "I2VAdapterTransformer2DModel":
+            patch(module, _make_transformer2d_forward(module, module.forward))
+        elif name == "TransformerTemporalModel":
+            patch(module, _make_temporal_forward(module, module.forward))
+    return undo

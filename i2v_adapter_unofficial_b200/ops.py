@@ -183,6 +183,81 @@ def reshard_unpack(x: torch.Tensor, world: int, inverse: bool = False, out: Opti
 
 
 # ----------------------------------------------------------------------------------------------------------
+# normalisation prologues, layout changes, residual epilogue (bf16, contiguous tensors)
+# ----------------------------------------------------------------------------------------------------------
+def _require_bf16_contig(*tensors: torch.Tensor) -> torch.device:
+    dev = _require_cuda(*tensors)
+    for t in tensors:
+        if t.dtype != torch.bfloat16:
+            raise TypeError(f"this kernel takes bfloat16 tensors, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError("this kernel takes contiguous tensors")
+    return dev
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+              pe: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm over the last axis; ``pe`` [F, C] is added per row with ``row % F`` (rows of a [N, F, C] tensor)."""
+    dev = _require_bf16_contig(x, weight, bias) if pe is None else _require_bf16_contig(x, weight, bias, pe)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if pe is not None and (pe.dim() != 2 or pe.shape[1] != C or x.dim() < 2 or x.shape[-2] != pe.shape[0]):
+        raise ValueError(f"pe {tuple(pe.shape)} does not match x {tuple(x.shape)}: need pe [x.shape[-2], C]")
+    y = torch.empty_like(x)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_layernorm_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                         None if pe is None else pe.data_ptr(), y.data_ptr(), rows, C,
+                                         0 if pe is None else pe.shape[0], float(eps), _stream(dev)))
+    return y
+
+
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    """x [..., 2*D] -> x[..., :D] * gelu(x[..., D:])."""
+    dev = _require_bf16_contig(x)
+    D = x.shape[-1] // 2
+    rows = x.numel() // (2 * D)
+    y = torch.empty(x.shape[:-1] + (D,), dtype=x.dtype, device=dev)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_geglu_fwd(x.data_ptr(), y.data_ptr(), rows, D, _stream(dev)))
+    return y
+
+
+def group_norm_tokens(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, eps: float,
+                      frames_per_stat: int = 1) -> torch.Tensor:
+    """GroupNorm of x [N, C, h, w] with statistics shared by ``frames_per_stat`` consecutive batch entries, written
+    token-major: [N, h*w, C] (frames_per_stat = 1) or [N/F * h*w, F, C] (frames_per_stat = F)."""
+    dev = _require_bf16_contig(x, weight, bias)
+    N, C, h, w = x.shape
+    S, fg = h * w, frames_per_stat
+    partial = torch.empty((N, groups, 2), dtype=torch.float32, device=dev)
+    out = (torch.empty((N, S, C), dtype=x.dtype, device=dev) if fg == 1
+           else torch.empty((N // fg * S, fg, C), dtype=x.dtype, device=dev))
+    lib = _lib.load()
+    with _on_device(dev):
+        st = _stream(dev)
+        _lib.check(lib.i2v_gn_stats(x.data_ptr(), partial.data_ptr(), N, C, S, groups, st))
+        _lib.check(lib.i2v_gn_apply_transpose(x.data_ptr(), partial.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                              out.data_ptr(), N, C, S, groups, fg, float(eps), st))
+    return out
+
+
+def tokens_to_nchw_residual(y: torch.Tensor, residual: torch.Tensor, frames_per_stat: int = 1) -> torch.Tensor:
+    """Inverse layout of ``group_norm_tokens`` plus the residual: y token-major, residual [N, C, h, w] -> [N, C, h, w]."""
+    dev = _require_bf16_contig(y, residual)
+    N, C, h, w = residual.shape
+    if y.numel() != residual.numel():
+        raise ValueError(f"y {tuple(y.shape)} and residual {tuple(residual.shape)} differ in size")
+    out = torch.empty_like(residual)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_untranspose_residual(y.data_ptr(), residual.data_ptr(), out.data_ptr(), N, C, h * w,
+                                                frames_per_stat, _stream(dev)))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 # torch.library registration: torch.ops.i2v_b200.*  (CUDA key only -> CPU tensors raise NotImplementedError)
 # ----------------------------------------------------------------------------------------------------------
 _torch_lib = None

@@ -375,14 +375,18 @@ class Installation:
     """Handle returned by ``install``: keeps the previous processors and hook handles for ``uninstall``."""
 
     def __init__(self, unet, previous: Dict[str, Any], hooks: List[Any], context: RuntimeContext,
-                 processors: Dict[str, Any]):
+                 processors: Dict[str, Any], undo_forwards: Optional[List[Any]] = None):
         self.unet = unet
         self.previous = previous
         self.hooks = hooks
         self.context = context
         self.processors = processors
+        self.undo_forwards = undo_forwards or []
 
     def uninstall(self) -> None:
+        for fn in reversed(self.undo_forwards):
+            fn()
+        self.undo_forwards = []
         for h in self.hooks:
             h.remove()
         self.hooks = []
@@ -430,9 +434,14 @@ def _bind_forward_args(module: nn.Module, args: Tuple, kwargs: Dict[str, Any]) -
         return dict(kwargs)
 
 
-def install(unet: nn.Module, mode: int = MODE_AUTO, fuse_cross_frame: bool = True) -> Installation:
+def install(unet: nn.Module, mode: int = MODE_AUTO, fuse_cross_frame: bool = True,
+            fast_path: bool = True) -> Installation:
     """Swap every attention processor of ``unet`` (a ``UNetMotionCrossFrameAttnModel`` — the reference's or
     ``hostmodel``'s — or any sub-module exposing ``attn_processors`` / ``set_attn_processor``) for the B200 ones.
+
+    ``fast_path=True`` additionally swaps the ``forward`` of the transformer wrappers / blocks around the attention
+    calls (``fastpath.py``: GroupNorm + layout change, LayerNorm (+ positional embedding), GEGLU, layout change +
+    residual in the library's bandwidth kernels); ``fast_path=False`` changes nothing but the processors.
 
     Must run *after* ``load_ip_adapter`` / ``_load_ip_adapter_weights`` because that call replaces all processors
     (reference :1246-1281); the IP-Adapter processors found are adopted, parameters shared."""
@@ -498,4 +507,9 @@ def install(unet: nn.Module, mode: int = MODE_AUTO, fuse_cross_frame: bool = Tru
         hooks.append(unet.register_forward_hook(unet_post))
 
     apply_attn_processors(unet, new)
-    return Installation(unet, previous, hooks, context, new)
+    undo_forwards = []
+    if fast_path:
+        from .fastpath import install_fast_forwards
+
+        undo_forwards = install_fast_forwards(unet)
+    return Installation(unet, previous, hooks, context, new, undo_forwards)

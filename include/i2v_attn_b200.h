@@ -112,6 +112,30 @@ int i2v_reshard_pack(const void* src, void* dst, int videos, int f_local, int se
 int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int seq_local, int channels, int world,
                        int elem_bytes, int inverse, void* stream);
 
+/* ---- normalisation prologues, layout changes and the residual epilogue around the attention operators ----
+ * (bf16 only; the reference runs them as separate PyTorch kernels: GroupNorm, permute+reshape copies, LayerNorm,
+ * `+ pos_embed`, GEGLU, residual add — src/modules/i2v_adapter.py:214-234, 298-314, 445-459, 514-525, 539-561 and
+ * diffusers TransformerTemporalModel.forward)
+ *
+ * i2v_layernorm_fwd: y[r, :] = LayerNorm(x[r, :]) * w + b (+ pe[r % pe_rows, :] when pe != NULL).  x, y: [rows, C]
+ *   contiguous, C % 8 == 0, C <= 2048.  pe: [pe_rows, C] (the sinusoidal table `pos_embed.pe[0, :F]`), rows ordered so
+ *   that r % pe_rows is the frame index ([B*S, F, C] of the motion module). */
+int i2v_layernorm_fwd(const void* x, const void* w, const void* b, const void* pe, void* y, long long rows, int C,
+                      int pe_rows, float eps, void* stream);
+/* i2v_geglu_fwd: y[r, c] = x[r, c] * gelu(x[r, D + c]) (erf GELU).  x: [rows, 2*D], y: [rows, D], D % 8 == 0. */
+int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream);
+/* GroupNorm + layout change in two passes over x [N, C, S] (NCHW, S = h*w), G groups, statistics shared by `fg`
+ * consecutive batch entries (fg = 1: the spatial transformer's per-frame GroupNorm; fg = num_frames: the motion module's
+ * GroupNorm over (C/G, F, h, w) per video, N = videos * fg, frame index fastest):
+ *   i2v_gn_stats:            partial[n, g] = (sum, sum of squares) of x[n, g*C/G : (g+1)*C/G, :]   (fp32, [N, G, 2])
+ *   i2v_gn_apply_transpose:  out[((v*S + s)*fg + f)*C + c] = GroupNorm(x)[v*fg + f, c, s]  -> (N, S, C) or (V*S, F, C)
+ *   i2v_untranspose_residual: out[n, c, s] = y[((v*S + s)*fg + f)*C + c] + res[n, c, s]    (the way back + residual)
+ * C % 64 == 0, S % 8 == 0, (C/G) % 2 == 0, (C/G)*S % 8 == 0. */
+int i2v_gn_stats(const void* x, float* partial, int N, int C, int S, int G, void* stream);
+int i2v_gn_apply_transpose(const void* x, const float* partial, const void* w, const void* b, void* out, int N, int C,
+                           int S, int G, int fg, float eps, void* stream);
+int i2v_untranspose_residual(const void* y, const void* res, void* out, int N, int C, int S, int fg, void* stream);
+
 /* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
  * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),
  * key 3: dense-attention tile variant + 1 for head dims <= 48 (see capi.cu). */

@@ -15,6 +15,8 @@ def main():
     stock = "--stock" in sys.argv
     dev = torch.device("cuda:0")
     unet = bench.build_unet(dev, torch.bfloat16)
+    if os.environ.get("CHANNELS_LAST") == "1":
+        unet = unet.to(memory_format=torch.channels_last)
     if not stock:
         install(unet)
     sched = DDIMScheduler()

@@ -1,0 +1,157 @@
+"""Normalisation / layout / epilogue kernels and the module-level fast path (-m gpu): each kernel through the C ABI
+against the CPU oracle arithmetic (fp32 PyTorch on the same bf16 inputs), then whole modules with
+``install(..., fast_path=True)`` against ``fast_path=False`` and the fp32 oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import SD15_HEADDIM_CFG, make_unet, randomize_zero_init, unet_inputs
+from i2v_adapter_unofficial_b200 import _lib, install, ops
+from i2v_adapter_unofficial_b200.hostmodel import (
+    I2VAdapterTransformer2DModel,
+    IPAdapterAttnProcessor2_0,
+    TransformerTemporalModel,
+)
+from oracle.attention_oracle import temporal_model_oracle, transformer2d_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(shape, seed, scale=1.0, shift=0.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale + shift).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("C", [320, 640, 1280, 64, 2048])
+@pytest.mark.parametrize("with_pe", [False, True])
+def test_layernorm_kernel(C, with_pe):
+    N, Fr = 37, 16
+    x = _rand((N, Fr, C), 1, 2.0, 0.5)
+    w, b = _rand((C,), 2, 0.2, 1.0), _rand((C,), 3, 0.2)
+    pe = _rand((Fr, C), 4) if with_pe else None
+    ref = F.layer_norm(x.float(), (C,), w.float(), b.float(), 1e-5)
+    if with_pe:
+        ref = ref.to(torch.bfloat16).float() + pe.float()   # the reference adds pos_embed to the bf16 LayerNorm output
+    got = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5, None if pe is None else pe.to(DEV)).float().cpu()
+    assert got.shape == x.shape
+    assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item() / 4)
+
+
+@pytest.mark.parametrize("D", [1280, 2560, 5120, 8])
+def test_geglu_kernel(D):
+    x = _rand((3, 50, 2 * D), 5, 1.5)
+    h, g = x.float().chunk(2, dim=-1)
+    ref = h * F.gelu(g)
+    got = ops.geglu(x.to(DEV)).float().cpu()
+    assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item() / 4)
+
+
+@pytest.mark.parametrize("case", [(6, 320, 16, 16, 1), (6, 320, 16, 16, 3), (4, 640, 8, 8, 2), (2, 1280, 12, 12, 2),
+                                  (32, 320, 64, 64, 16), (3, 64, 4, 2, 1)], ids=str)
+def test_group_norm_tokens_and_back(case):
+    N, C, h, w, fg = case
+    x = _rand((N, C, h, w), 6, 1.5, 0.3)
+    wt, bs = _rand((C,), 7, 0.2, 1.0), _rand((C,), 8, 0.2)
+    V, S = N // fg, h * w
+    xf = x.float().view(V, fg, C, h, w).permute(0, 2, 1, 3, 4)          # statistics over (C/G, fg, h, w)
+    ref = F.group_norm(xf, 32, wt.float(), bs.float(), 1e-6)             # [V, C, fg, h, w]
+    ref_tok = ref.permute(0, 3, 4, 2, 1).reshape(V * S, fg, C)          # (B*S, F, C) as TransformerTemporalModel does
+    tok = ops.group_norm_tokens(x.to(DEV), wt.to(DEV), bs.to(DEV), 32, 1e-6, fg)
+    exp_shape = (N, S, C) if fg == 1 else (V * S, fg, C)
+    assert tuple(tok.shape) == exp_shape
+    assert (tok.float().cpu().view(V * S, fg, C) - ref_tok).abs().max().item() <= 3e-2
+    # way back + residual: out[n, c, s] = y[token layout] + res
+    y = _rand(tuple(tok.shape), 9)
+    res = _rand((N, C, h, w), 10)
+    back = ops.tokens_to_nchw_residual(y.to(DEV), res.to(DEV), fg).float().cpu()
+    ref_back = (y.float().view(V, h, w, fg, C).permute(0, 3, 4, 1, 2).reshape(N, C, h, w) + res.float())
+    assert (back - ref_back).abs().max().item() <= 2e-2
+
+
+def test_layout_kernels_reject_unsupported_shapes():
+    x = torch.zeros(2, 100, 4, 4, device=DEV, dtype=torch.bfloat16)     # C % 64 != 0
+    w = torch.ones(100, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.I2VLibraryError) as e:
+        ops.group_norm_tokens(x, w, w, 4, 1e-6, 1)
+    assert e.value.code == -2
+    with pytest.raises(TypeError):
+        ops.layernorm(torch.zeros(4, 64, device=DEV), torch.ones(64, device=DEV), torch.zeros(64, device=DEV))
+
+
+def _sd(module, prefix):
+    return {f"{prefix}.{k}": v.float().cpu() for k, v in module.state_dict().items()}
+
+
+def test_spatial_transformer_fast_path_matches_oracle_and_slow_path():
+    torch.manual_seed(0)
+    C, H, Fr, V, hw = 320, 8, 4, 2, 16
+    m = I2VAdapterTransformer2DModel(num_attention_heads=H, attention_head_dim=C // H, in_channels=C,
+                                     norm_num_groups=32, cross_attention_dim=768).eval()
+    for tb in m.transformer_blocks:
+        tb.attn2.set_processor(IPAdapterAttnProcessor2_0(C, 768, num_tokens=4, scale=1.0))
+    randomize_zero_init(m)
+    x = torch.randn(V * Fr, C, hw, hw)
+    ctx = torch.randn(V, 81, 768).repeat_interleave(Fr, dim=0)
+    with torch.no_grad():
+        ref = transformer2d_oracle(_sd(m, "t"), "t", x, ctx, H, 32, True, Fr, 4, 1.0)
+    m = m.to(DEV, torch.bfloat16)
+    outs = {}
+    for fast in (False, True):
+        handle = install(m, fast_path=fast)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            outs[fast] = m(x.to(DEV, torch.bfloat16), enable_cross_frame_attn=True,
+                           encoder_hidden_states=ctx.to(DEV, torch.bfloat16), num_frames=Fr).sample.float().cpu()
+        launches = _lib.launch_count() - n0
+        handle.uninstall()
+        # fast path: + gn_stats, gn_apply_transpose, 3 layernorm, geglu, untranspose_residual
+        assert launches == (2 + 7 if fast else 2)
+    for fast in (False, True):
+        cos = F.cosine_similarity(outs[fast].flatten(), ref.flatten(), dim=0).item()
+        assert cos >= 0.999, (fast, cos)
+    scale = ref.abs().max().item()
+    assert (outs[True] - ref).abs().max().item() <= 1.5 * max((outs[False] - ref).abs().max().item(), 0.01 * scale)
+
+
+def test_temporal_module_fast_path_matches_oracle_and_slow_path():
+    torch.manual_seed(1)
+    m = TransformerTemporalModel(num_attention_heads=8, attention_head_dim=40, in_channels=320, norm_num_groups=32,
+                                 positional_embeddings="sinusoidal", num_positional_embeddings=32).eval()
+    randomize_zero_init(m)
+    x = torch.randn(2 * 16, 320, 8, 8)
+    with torch.no_grad():
+        ref = temporal_model_oracle(_sd(m, "m"), "m", x, 16, 8, 32)
+    m = m.to(DEV, torch.bfloat16)
+    outs = {}
+    for fast in (False, True):
+        handle = install(m, fast_path=fast)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            outs[fast] = m(x.to(DEV, torch.bfloat16), num_frames=16)[0].float().cpu()
+        launches = _lib.launch_count() - n0
+        handle.uninstall()
+        assert launches == (2 + 7 if fast else 2)
+        cos = F.cosine_similarity(outs[fast].flatten(), ref.flatten(), dim=0).item()
+        assert cos >= 0.999 and (outs[fast] - ref).abs().max().item() <= 5e-2, (fast, cos)
+
+
+def test_unet_fast_path_equals_processor_only_path():
+    """Whole UNet (SD1.5 head dims), bf16: fast path vs processors only vs the fp32 oracle."""
+    from oracle.unet_oracle import unet_oracle
+
+    unet = randomize_zero_init(make_unet(SD15_HEADDIM_CFG, ip_adapter=True))
+    sample, ctx, img = unet_inputs(unet, videos=1, frames=4, size=32, tokens=77, image_embed_dim=64)
+    with torch.no_grad():
+        ref = unet_oracle(dict(unet.state_dict()), dict(unet.config), sample, 37, True, ctx, img)
+    unet = unet.to(DEV, torch.bfloat16)
+    outs = {}
+    for fast in (False, True):
+        handle = install(unet, fast_path=fast)
+        with torch.no_grad():
+            outs[fast] = unet(sample.to(DEV, torch.bfloat16), 37, True, ctx.to(DEV, torch.bfloat16),
+                              added_cond_kwargs={"image_embeds": img.to(DEV, torch.bfloat16)}).sample.float().cpu()
+        handle.uninstall()
+    cos = {k: F.cosine_similarity(v.flatten(), ref.flatten(), dim=0).item() for k, v in outs.items()}
+    assert cos[True] >= 0.999 and cos[False] >= 0.999, cos
+    assert cos[True] >= cos[False] - 2e-4

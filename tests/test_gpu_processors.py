@@ -82,7 +82,7 @@ def test_temporal_module_bf16():
     with torch.no_grad():
         ref = temporal_model_oracle(_sd(m, "m"), "m", x, 16, 8, 32)
     m = m.to(DEV, torch.bfloat16)
-    install(m)
+    install(m, fast_path=False)
     n0 = _lib.launch_count()
     with torch.no_grad():
         out = m(_bf16(x), num_frames=16)[0].float().cpu()
