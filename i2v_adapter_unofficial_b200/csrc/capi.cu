@@ -283,12 +283,15 @@ int check_common(int batch, int heads, int sq, int skv, int d, int dtype, int mo
 template <int D, int HG, int FT>
 int launch_temporal_cfg(const i2v::TemporalParams& P, int sms, cudaStream_t stream) {
   using Cfg = i2v::TemporalCfg<D, HG, FT>;
-  // Two co-resident CTAs per SM (16 consumer warps) when two 2..3-stage rings fit; otherwise one CTA with up to 4 stages.
+  // As many co-resident CTAs per SM as 2-stage rings fit (up to 3: measured best, 5.8 TB/s at d = 40 against 4.5 with
+  // two and 2.5 with one); a lone CTA gets a deeper ring instead.
   const int budget = 226 * 1024;
   const int ring_overhead = 256 + 128;
-  int per_sm = g_tuning[1] > 0 ? g_tuning[1] : ((2 * (2 * Cfg::STAGE_BYTES + ring_overhead + 1024) <= budget) ? 2 : 1);
-  int stages = g_tuning[0] > 0 ? g_tuning[0] : (per_sm >= 2 ? 3 : 4);
-  while (stages > 2 && per_sm * (stages * Cfg::STAGE_BYTES + ring_overhead + 1024) > budget) --stages;
+  auto fits = [&](int ctas, int stages) { return ctas * (stages * Cfg::STAGE_BYTES + ring_overhead + 1024) <= budget; };
+  int per_sm = g_tuning[1] > 0 ? g_tuning[1] : (fits(3, 2) ? 3 : (fits(2, 2) ? 2 : 1));
+  int stages = g_tuning[0] > 0 ? g_tuning[0] : (per_sm >= 2 ? 2 : 4);
+  while (stages > 2 && !fits(per_sm, stages)) --stages;
+  while (per_sm > 1 && !fits(per_sm, stages)) --per_sm;
   if (stages > 8) stages = 8;
   const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + ring_overhead;
   if (smem > 227 * 1024) return fail(I2V_ERR_UNSUPPORTED, "temporal stage (%d B) does not fit shared memory", Cfg::STAGE_BYTES);
@@ -304,11 +307,21 @@ int launch_temporal_cfg(const i2v::TemporalParams& P, int sms, cudaStream_t stre
 }
 
 // heads per staged unit: keep a stage (3 slabs of FT*16 rows) around 32-64 KB so >= 2 stages always fit
-template <int D, int FT> struct TemporalHG { static constexpr int value = (FT == 1) ? (D <= 80 ? 8 : 4) : (D <= 40 ? 8 : (D <= 80 ? 4 : 2)); };
+// (measured: 3 resident CTAs with ~31 KB stages beat fewer CTAs with larger stages: d=80 4.9 TB/s at HG=4 vs 4.2 at HG=8)
+template <int D, int FT> struct TemporalHG { static constexpr int value = (FT == 1) ? (D <= 40 ? 8 : 4) : (D <= 40 ? 8 : (D <= 80 ? 4 : 2)); };
 
 template <int D>
 int launch_temporal_ft(const i2v::TemporalParams& P, int sms, cudaStream_t stream) {
-  if (P.frames <= 16) return launch_temporal_cfg<D, TemporalHG<D, 1>::value, 1>(P, sms, stream);
+  // tuning key 4: heads per staged unit override for experiments (must divide 8 and keep D/8 output tiles splittable)
+  if (P.frames <= 16) {
+    if constexpr (D == 80 || D == 64) {
+      if (g_tuning[4] == 8) return launch_temporal_cfg<D, 8, 1>(P, sms, stream);
+    }
+    if constexpr (D == 160 || D == 128) {
+      if (g_tuning[4] == 2) return launch_temporal_cfg<D, 2, 1>(P, sms, stream);
+    }
+    return launch_temporal_cfg<D, TemporalHG<D, 1>::value, 1>(P, sms, stream);
+  }
   return launch_temporal_cfg<D, TemporalHG<D, 2>::value, 2>(P, sms, stream);
 }
 
