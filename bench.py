@@ -37,6 +37,10 @@ FRAMES, LATENT, GUIDANCE, DDIM_STEPS = 16, 64, 7.5, 25
 SD15 = dict(block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, cross_attention_dim=768,
             num_attention_heads=8, motion_num_attention_heads=8, motion_max_seq_length=32, norm_num_groups=32)
 IMAGE_EMBED_DIM = 1024
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01_dense_attn_l0.md, profiles/r01_temporal_attn_l0.md); null until a capture exists
+TRAFFIC_DENSE_L0_BYTES = 493.0e6
+TRAFFIC_TEMPORAL_L0_BYTES = 314.7e6
 
 
 def _peaks():
@@ -204,38 +208,37 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
-class DominantKernelTimer:
-    """CUDA-event pairs around the level-0 fused self + cross-frame attention launches (the dominant kernel)."""
+class KernelTimer:
+    """CUDA-event pairs (on the launching stream) around the launches of one ops.* entry whose first argument has
+    ``shape[1] == match`` — the level-0 instances of the fused self + cross-frame attention (the dominant kernel) and
+    of the temporal attention."""
 
-    def __init__(self, ops_mod, seq):
-        self.ops = ops_mod
-        self.seq = seq
+    def __init__(self, ops_mod, name, match):
+        self.ops, self.name, self.match = ops_mod, name, match
         self.pairs = []
         self.enabled = False
-        self._orig = ops_mod.fused_self_xframe
+        self._orig = getattr(ops_mod, name)
 
     def install(self):
         import torch
 
-        def wrapped(q_self, *a, **kw):
-            if self.enabled and q_self.shape[1] == self.seq:
+        def wrapped(first, *a, **kw):
+            if self.enabled and first.shape[1] == self.match[1] and first.shape[0] == self.match[0]:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                out = self._orig(q_self, *a, **kw)
+                out = self._orig(first, *a, **kw)
                 e1.record()
-                self.pairs.append((e0, e1, q_self.shape))
+                self.pairs.append((e0, e1, tuple(first.shape)))
                 return out
-            return self._orig(q_self, *a, **kw)
+            return self._orig(first, *a, **kw)
 
-        self.ops.fused_self_xframe = wrapped
+        setattr(self.ops, self.name, wrapped)
 
     def summary(self):
         if not self.pairs:
             return None
         ms = [a.elapsed_time(b) for a, b, _ in self.pairs]
-        bf, s, h, d = self.pairs[0][2]
-        flops = 2 * 4.0 * bf * h * s * s * d  # self + cross-frame, true head dim, softmax not counted
-        return dict(avg_ms=sum(ms) / len(ms), launches=len(ms), flops_per_launch=flops)
+        return dict(avg_ms=sum(ms) / len(ms), launches=len(ms), shape=self.pairs[0][2])
 
 
 def run_b200(args, rank, world, local_rank):
@@ -254,8 +257,10 @@ def run_b200(args, rank, world, local_rank):
     sched.set_timesteps(DDIM_STEPS, device="cpu")
     ts = [int(t) for t in sched.timesteps]
 
-    timer = DominantKernelTimer(ops, LATENT * LATENT)
+    timer = KernelTimer(ops, "fused_self_xframe", (2 * FRAMES, LATENT * LATENT))       # [BF, S, H, d] at level 0
     timer.install()
+    ttimer = KernelTimer(ops, "temporal_attn", (2 * LATENT * LATENT, FRAMES))           # [B*S, F, H, d] at level 0
+    ttimer.install()
 
     host = make_inputs(1, FRAMES, LATENT, seed=1 + rank, dtype=dtype, pin=True)
     d_in = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -277,7 +282,7 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    timer.enabled = True
+    timer.enabled = ttimer.enabled = True
     if args.profiler_range:  # `ncu --profile-from-start off`: only the timed steps are captured
         torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -288,7 +293,7 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     if args.profiler_range:
         torch.cuda.profiler.stop()
-    timer.enabled = False
+    timer.enabled = ttimer.enabled = False
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -330,12 +335,27 @@ def run_b200(args, rank, world, local_rank):
     dom = timer.summary()
     roofline = None
     if dom is not None:
-        achieved = dom["flops_per_launch"] / (dom["avg_ms"] * 1e-3) / 1e12
-        roofline = dict(bound="tensor", kernel="dense_attn_kernel<DK=48> (fused spatial self + cross-frame, level 0: "
-                        "S=4096, d=40, 32 frames x 8 heads x 2 problems)", achieved=achieved, peak=peaks["tflops"],
-                        unit="TFLOP/s", frac=achieved / peaks["tflops"], peak_source=f"{peaks['source']} sustained bf16",
+        bf, s_, h_, d_ = dom["shape"]
+        flops = 2 * 4.0 * bf * h_ * s_ * s_ * d_  # self + cross-frame, true head dim (40), softmax not counted
+        achieved = flops / (dom["avg_ms"] * 1e-3) / 1e12
+        roofline = dict(bound="tensor", kernel="dense_attn_kernel<DK=48, BN=64> (fused spatial self + cross-frame, "
+                        "level 0: S=4096, d=40, 32 frames x 8 heads x 2 problems)", achieved=achieved,
+                        peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"],
+                        peak_source=f"{peaks['source']} sustained bf16 (kernel timed inside the step)",
                         frac_of_nominal_2250=achieved / 2250.0, avg_launch_ms=dom["avg_ms"],
-                        launches_timed=dom["launches"], flops_per_launch=dom["flops_per_launch"], traffic=None)
+                        launches_timed=dom["launches"], flops_per_launch=flops,
+                        traffic=TRAFFIC_DENSE_L0_BYTES)
+    tdom = ttimer.summary()
+    roofline_temporal = None
+    if tdom is not None:
+        n_, f_, h_, d_ = tdom["shape"]
+        nbytes = 4.0 * n_ * f_ * h_ * d_ * 2  # read Q, K, V, write O once (bf16)
+        gbs = nbytes / (tdom["avg_ms"] * 1e-3) / 1e9
+        roofline_temporal = dict(bound="hbm", kernel="temporal_attn_kernel<d=40, HG=8> (motion module, level 0: "
+                                 "8192 positions x 16 frames x 8 heads)", achieved=gbs, peak=peaks["hbm"], unit="GB/s",
+                                 frac=gbs / peaks["hbm"], peak_source=f"{peaks['source']} copy bandwidth",
+                                 avg_launch_ms=tdom["avg_ms"], launches_timed=tdom["launches"],
+                                 bytes_per_launch=nbytes, traffic=TRAFFIC_TEMPORAL_L0_BYTES)
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         handle.uninstall()
@@ -349,9 +369,11 @@ def run_b200(args, rank, world, local_rank):
                                      "adapter + I2V-Adapter + IP-Adapter, 1 video x CFG per GPU, 16 frames, 64x64 "
                                      "latent, DDIM 25 timesteps",
                             parallelism=f"dp{world} (independent videos, no collective)",
+                            processors="install(unet, fast_path=True): B200 processors + module-level fast path",
                             l2="working set >> 126 MB L2 (2.7 GB bf16 weights, 84 MB activations per level-0 tensor)"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_base, clocks=clocks)
+                gpu_launches=int(launches), roofline=roofline, roofline_temporal=roofline_temporal,
+                cpu_baseline=cpu_base, clocks=clocks)
     print(json.dumps(line), flush=True)
 
 

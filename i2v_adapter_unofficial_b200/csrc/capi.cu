@@ -159,7 +159,8 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
   // tile variant for d <= 48 (tuning key 3, value - 1): 0 = two 128x128 tiles, one CTA per SM; 1 (default) = two 128x64
   // tiles per CTA, two CTAs per SM; 2 = four 128x64 tiles per CTA, each warpgroup alternating between two
   const int variant = g_tuning[3] > 0 ? g_tuning[3] - 1 : 1;
-  const int bn = (dk == 48 && variant >= 1 && seg_split < 0) ? 64 : dense_block_n(dk);
+  // two-segment (IP-Adapter) launches keep all keys in one 128-key tile; at d = 160 that takes the single-query-tile config
+  const int bn = seg_split >= 0 ? 128 : ((dk == 48 && variant >= 1) ? 64 : dense_block_n(dk));
   if (seg_split >= 0 && skv > bn)
     return fail(I2V_ERR_UNSUPPORTED, "two-segment softmax needs skv (%d) <= %d", skv, bn);
   i2v::DenseParams P;
@@ -222,7 +223,9 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
       }
     case 96:  return launch_dense_cfg<i2v::DenseCfg<96, 128, 2>>(P, stream);
     case 128: return launch_dense_cfg<i2v::DenseCfg<128, 128, 2>>(P, stream);
-    case 160: return launch_dense_cfg<i2v::DenseCfg<160, 64, 2>>(P, stream);
+    case 160:
+      if (bn == 128) return launch_dense_cfg<i2v::DenseCfg<160, 128, 1, 0, 1, 1, 0, 1>>(P, stream);
+      return launch_dense_cfg<i2v::DenseCfg<160, 64, 2>>(P, stream);
   }
   return fail(I2V_ERR_UNSUPPORTED, "head dim %d not covered by the tcgen05 kernels", d);
 }
@@ -424,7 +427,7 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
       k_ip->stride_b == k_txt->stride_b && k_ip->stride_s == k_txt->stride_s && k_ip->stride_h == k_txt->stride_h &&
       v_ip->stride_b == v_txt->stride_b && v_ip->stride_s == v_txt->stride_s && v_ip->stride_h == v_txt->stride_h;
   const bool fast_ok =
-      dense_supported(d, dtype) && contiguous_tokens && (n_txt + n_ip) <= dense_block_n(dense_dk(d));
+      dense_supported(d, dtype) && contiguous_tokens && (n_txt + n_ip) <= 128;
   if (mode == I2V_MODE_FAST && !fast_ok)
     return fail(I2V_ERR_UNSUPPORTED,
                 "i2v_ip_xattn_fwd: FAST path needs bf16, supported head dim, image tokens stored right after the text "

@@ -61,10 +61,10 @@ struct DenseParams {
 // EMU_ = how many of every 8 (key, key+1) pairs get their 2^x from the FMA-pipe polynomial instead of MUFU.EX2.
 // At d = 40 the kernel is exp-bound (16384 exps per 128x128 tile at 16 MUFU/clk/SM = 1024 clk against 384 clk of
 // MMA), so part of the exponentials is moved to the otherwise idle FMA pipe.
-template <int DK_, int BLOCK_N_, int NSTAGES_, int EMU_ = 0, int MIN_CTAS_ = 1, int TPW_ = 1, int NMW_ = 0>
+template <int DK_, int BLOCK_N_, int NSTAGES_, int EMU_ = 0, int MIN_CTAS_ = 1, int TPW_ = 1, int NMW_ = 0, int NT_ = 0>
 struct DenseCfg {
   static constexpr int TPW = TPW_;      // query tiles per softmax warpgroup
-  static constexpr int NT = 2 * TPW_;   // query tiles per CTA
+  static constexpr int NT = NT_ > 0 ? NT_ : 2 * TPW_;   // query tiles per CTA (NT_ = 1: a single tile, warpgroup 1 idles)
   static constexpr int NMW = NMW_ > 0 ? NMW_ : NT;  // MMA-issuing warps (tile t is issued by warp t % NMW)
   static constexpr int THREADS = (9 + NMW) * 32;
   static constexpr int EMU = EMU_;

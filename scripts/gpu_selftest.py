@@ -139,6 +139,7 @@ def group_ip():
     torch.manual_seed(4)
     ok = True
     for (B, H, Sq, d, g, nt, ni) in ((4, 8, 256, 40, 2, 77, 4), (2, 8, 1024, 80, 1, 77, 4), (2, 8, 64, 160, 2, 50, 14),
+                                     (4, 8, 256, 160, 2, 77, 4), (2, 8, 200, 160, 1, 100, 28),
                                      (32, 8, 4096, 40, 16, 77, 4)):
         q = torch.randn(B, Sq, H, d, device="cuda", dtype=torch.bfloat16)
         k = torch.randn(B // g, nt + ni, H, d, device="cuda", dtype=torch.bfloat16)
