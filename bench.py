@@ -39,8 +39,8 @@ SD15 = dict(block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, cross
 IMAGE_EMBED_DIM = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/r01_dense_attn_l0.md, profiles/r01_temporal_attn_l0.md); null until a capture exists
-TRAFFIC_DENSE_L0_BYTES = 493.0e6
-TRAFFIC_TEMPORAL_L0_BYTES = 314.7e6
+TRAFFIC_DENSE_L0_BYTES = 496.4e6
+TRAFFIC_TEMPORAL_L0_BYTES = 312.1e6
 
 
 def _peaks():
@@ -270,7 +270,15 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None
+    if args.graph:
+        from i2v_adapter_unofficial_b200.graph import GraphedDenoiser
+
+        graphed = GraphedDenoiser(unet, sched, d_in["latents"], d_in["prompt"], GUIDANCE, d_in["cond"], d_in["image"])
+
     def one_step(i, latents):
+        if graphed is not None:
+            return graphed.step(i)  # latents live in the graph's static buffer
         return denoise_step(unet, sched, latents, ts[i % len(ts)], d_in["prompt"], GUIDANCE, d_in["cond"], d_in["image"])
 
     # ---- value: inputs resident in HBM ----
@@ -295,6 +303,8 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.profiler.stop()
     timer.enabled = ttimer.enabled = False
     launches = _lib.launch_count() - launches0
+    if graphed is not None:
+        launches = graphed.launches_per_step * args.steps  # recorded at capture; replays do not pass through the host
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -307,6 +317,10 @@ def run_b200(args, rank, world, local_rank):
     d2h = out_host.numel() * out_host.element_size()
 
     def e2e_step(i):
+        if graphed is not None:
+            graphed.load_inputs(host["latents"], host["prompt"], host["cond"], host["image"])  # H2D from pinned memory
+            out_host.copy_(graphed.step(i), non_blocking=True)
+            return
         din = {k: host[k].to(dev, non_blocking=True) for k in ("latents", "cond", "prompt", "image")}
         new = denoise_step(unet, sched, din["latents"], ts[i % len(ts)], din["prompt"], GUIDANCE, din["cond"],
                            din["image"])
@@ -327,6 +341,14 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms_total = ms2.item()
 
+    if graphed is not None:
+        # events cannot bracket nodes of a replayed graph: time the two level-0 kernels in an eager pass of the same step
+        timer.enabled = ttimer.enabled = True
+        lat_e = d_in["latents"].clone()
+        for i in range(2):
+            lat_e = denoise_step(unet, sched, lat_e, ts[i], d_in["prompt"], GUIDANCE, d_in["cond"], d_in["image"])
+        torch.cuda.synchronize()
+        timer.enabled = ttimer.enabled = False
     if rank != 0:
         return
     peaks = _peaks()
@@ -370,6 +392,7 @@ def run_b200(args, rank, world, local_rank):
                                      "latent, DDIM 25 timesteps",
                             parallelism=f"dp{world} (independent videos, no collective)",
                             processors="install(unet, fast_path=True): B200 processors + module-level fast path",
+                            launch="CUDA graph replay" if graphed is not None else "eager",
                             l2="working set >> 126 MB L2 (2.7 GB bf16 weights, 84 MB activations per level-0 tensor)"),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=int(launches), roofline=roofline, roofline_temporal=roofline_temporal,
@@ -385,6 +408,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="developer runs under a profiler: skip the host-buffer leg")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay a captured CUDA graph of the denoise step (i2v_adapter_unofficial_b200.graph) in both "
+                         "timed regions; per-kernel rooflines are then timed in an eager pass after them")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
