@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "i2v_launch_count",
     "i2v_sdpa_fwd",
     "i2v_fused_self_xframe_fwd",
+    "i2v_fused_self_xframe_aug_fwd",
     "i2v_ip_xattn_fwd",
     "i2v_temporal_attn_fwd",
     "i2v_reshard_pack",
@@ -76,6 +77,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_sdpa_fwd.argtypes = [T, T, T, T, i, i, i, i, i, i, f, i, i, p]
     lib.i2v_fused_self_xframe_fwd.restype = i
     lib.i2v_fused_self_xframe_fwd.argtypes = [T, T, T, T, T, T, T, T, i, i, i, i, i, f, i, i, p]
+    lib.i2v_fused_self_xframe_aug_fwd.restype = i
+    lib.i2v_fused_self_xframe_aug_fwd.argtypes = [T, T, T, T, T, T, T, T, i, i, i, i, i, i, i, p]
     lib.i2v_ip_xattn_fwd.restype = i
     lib.i2v_ip_xattn_fwd.argtypes = [T, T, T, T, T, T, i, i, i, i, i, i, i, f, f, i, i, p]
     lib.i2v_temporal_attn_fwd.restype = i

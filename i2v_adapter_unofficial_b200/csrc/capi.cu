@@ -9,6 +9,7 @@
 
 #include "../../include/i2v_attn_b200.h"
 #include "dense_attn_sm100.cuh"
+#include "dense_attn_pipe_sm100.cuh"
 #include "generic_attn.cuh"
 #include "norm_layout.cuh"
 #include "temporal_attn.cuh"
@@ -151,6 +152,26 @@ int launch_dense_cfg(const i2v::DenseParams& Pin, cudaStream_t stream) {
   return 0;
 }
 
+template <class Cfg>
+int launch_dense_pipe_cfg(const i2v::DenseParams& Pin, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = i2v::dense_attn_pipe_kernel<Cfg>;
+  if (!attr_set[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev & 63] = true;
+  }
+  i2v::DenseParams P = Pin;
+  P.q_blocks = (P.sq + 128 * Cfg::NT - 1) / (128 * Cfg::NT);
+  const long long grid = (long long)P.q_blocks * P.heads * P.batch * P.nprob;
+  if (grid <= 0 || grid > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "dense attention grid %lld out of range", grid);
+  kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
 int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, int skv, int d, float scale,
                  int seg_split, float seg_scale, cudaStream_t stream) {
   int rc = get_encode_fn();
@@ -158,9 +179,11 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
   const int dk = dense_dk(d);
   // tile variant for d <= 48 (tuning key 3, value - 1): 0 = two 128x128 tiles, one CTA per SM; 1 (default) = two 128x64
   // tiles per CTA, two CTAs per SM; 2 = four 128x64 tiles per CTA, each warpgroup alternating between two
-  const int variant = g_tuning[3] > 0 ? g_tuning[3] - 1 : 1;
+  const int variant = g_tuning[3] > 0 ? g_tuning[3] - 1 : 4;
   // two-segment (IP-Adapter) launches keep all keys in one 128-key tile; at d = 160 that takes the single-query-tile config
-  const int bn = seg_split >= 0 ? 128 : ((dk == 48 && variant >= 1) ? 64 : dense_block_n(dk));
+  // variants 3 / 4: software-pipelined kernel (dense_attn_pipe_sm100.cuh), 4 tiles x 48 keys / 3 tiles x 64 keys
+  const bool pipe = dk == 48 && seg_split < 0 && variant >= 3;
+  const int bn = seg_split >= 0 ? 128 : (pipe ? (variant == 3 ? 48 : 64) : ((dk == 48 && variant >= 1) ? 64 : dense_block_n(dk)));
   if (seg_split >= 0 && skv > bn)
     return fail(I2V_ERR_UNSUPPORTED, "two-segment softmax needs skv (%d) <= %d", skv, bn);
   i2v::DenseParams P;
@@ -193,6 +216,22 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
     case 16:  return launch_dense_cfg<i2v::DenseCfg<16, 128, 4>>(P, stream);
     case 32:  return launch_dense_cfg<i2v::DenseCfg<32, 128, 4>>(P, stream);
     case 48:
+      if (pipe && variant == 3) {
+        switch (emu) {
+          case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 0, 3, 3>>(P, stream);
+          case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 2, 3, 3>>(P, stream);
+          case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 4, 3, 3>>(P, stream);
+          default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 3, 3, 3>>(P, stream);
+        }
+      }
+      if (pipe) {
+        switch (emu) {
+          case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0>>(P, stream);
+          case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2>>(P, stream);
+          case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4>>(P, stream);
+          default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3>>(P, stream);
+        }
+      }
       if (bn == 64 && variant == 2) {  // four query tiles per CTA, each warpgroup alternates between two
         switch (emu) {
           case 0:  return launch_dense_cfg<i2v::DenseCfg<48, 64, 4, 0, 1, 2>>(P, stream);
@@ -408,6 +447,60 @@ int i2v_fused_self_xframe_fwd(const i2v_tensor* q_self, const i2v_tensor* k_self
   if (rc) return rc;
   return launch_generic(q_x, k_x, v_x, o_x, nullptr, nullptr, batch, heads, seq, seq, 0, d, num_frames, scale, 0.f,
                         dtype, (cudaStream_t)stream);
+}
+
+int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_self, const i2v_tensor* v_self,
+                                  const i2v_tensor* o_self, const i2v_tensor* q_x, const i2v_tensor* k_x,
+                                  const i2v_tensor* v_x, const i2v_tensor* o_x, int batch, int heads, int seq, int d,
+                                  int d_pad, int num_frames, int dtype, void* stream) {
+  int rc = check_common(batch, heads, seq, seq, d, dtype, I2V_MODE_FAST);
+  if (rc) return rc;
+  if (num_frames <= 0) return fail(I2V_ERR_BAD_SHAPE, "`num_frames` must be provided when `enable_cross_frame_attn` is True.");
+  if (batch % num_frames)
+    return fail(I2V_ERR_BAD_SHAPE, "Batch size %d must be divisible by the number of frames %d.", batch, num_frames);
+  if (dtype != I2V_BF16 || d != i2v::kAugCol || d_pad != 48)
+    return fail(I2V_ERR_UNSUPPORTED, "i2v_fused_self_xframe_aug_fwd: bf16, d = %d stored padded to 48 only (got d=%d d_pad=%d)",
+                i2v::kAugCol, d, d_pad);
+  DeviceInfo* di = nullptr;
+  if ((rc = device_info(&di))) return rc;
+  if ((rc = get_encode_fn())) return rc;
+  const int variant = g_tuning[3] > 0 ? g_tuning[3] - 1 : 4;
+  const int bn = variant == 3 ? 48 : 64;
+  i2v::DenseParams P;
+  memset(&P, 0, sizeof(P));
+  P.nprob = 2;
+  P.batch = batch; P.heads = heads; P.sq = seq; P.skv = seq; P.d = d;
+  P.scale_log2e = 1.f;
+  P.seg_split = -1;
+  const DenseSeg segs[2] = {{q_self, k_self, v_self, o_self, 1}, {q_x, k_x, v_x, o_x, num_frames}};
+  for (int i = 0; i < 2; ++i) {
+    const DenseSeg& s = segs[i];
+    if ((rc = check_tensor("q", s.q, 2, true)) || (rc = check_tensor("k", s.k, 2, true)) ||
+        (rc = check_tensor("v", s.v, 2, true)) || (rc = check_tensor("o", s.o, 2, true)))
+      return rc;
+    if ((rc = make_tmap(&P.prob[i].tm_q, s.q, batch, seq, heads, d_pad, 128))) return rc;
+    if ((rc = make_tmap(&P.prob[i].tm_k, s.k, batch / s.kv_group, seq, heads, d_pad, bn))) return rc;
+    if ((rc = make_tmap(&P.prob[i].tm_v, s.v, batch / s.kv_group, seq, heads, d_pad, bn))) return rc;
+    P.prob[i].o = reinterpret_cast<__nv_bfloat16*>(s.o->data);
+    P.prob[i].o_sb = s.o->stride_b; P.prob[i].o_ss = s.o->stride_s; P.prob[i].o_sh = s.o->stride_h;
+    P.prob[i].kv_group = s.kv_group;
+  }
+  const int emu = g_tuning[2] > 0 ? g_tuning[2] - 1 : -1;
+  if (variant == 3) {
+    switch (emu) {
+      case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 0, 3, 3, true>>(P, (cudaStream_t)stream);
+      case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 2, 3, 3, true>>(P, (cudaStream_t)stream);
+      case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 4, 3, 3, true>>(P, (cudaStream_t)stream);
+      default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 3, 3, 3, true>>(P, (cudaStream_t)stream);
+    }
+  }
+  switch (emu) {
+    case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, 0, true>>(P, (cudaStream_t)stream);
+    case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, 0, true>>(P, (cudaStream_t)stream);
+    case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, 0, true>>(P, (cudaStream_t)stream);
+    case 5:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 2, 0, true>>(P, (cudaStream_t)stream);
+    default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, 0, true>>(P, (cudaStream_t)stream);
+  }
 }
 
 int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_tensor* v_txt, const i2v_tensor* k_ip,

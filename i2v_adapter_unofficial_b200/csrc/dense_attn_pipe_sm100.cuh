@@ -1,0 +1,477 @@
+// Software-pipelined dense attention forward for small head dims (d <= 48: SD1.5 level 0, d = 40) on sm_100a.
+//
+// Same operator and launch contract as dense_attn_sm100.cuh (K1 spatial self-attention + K2 I2V-Adapter cross-frame
+// attention of src/modules/i2v_adapter.py:468-492 in one launch), different schedule.  At d = 40 a 128 x BN score
+// tile costs 3x more exponential time than MMA time, so the kernel is bound by the softmax warps; what the first
+// kernel loses is that a softmax warpgroup idles through a full tensor round trip every KV tile
+// (P(j) -> PV(j) -> QK(j+1) -> S(j+1): ~1400 clk of latency against ~500 clk of work, measured with the in-kernel
+// timeline).  Here P gets its own TMEM columns instead of aliasing S, which breaks that chain:
+//
+//   softmax warpgroup t                                    MMA warp of tile t
+//   wait S(j); tcgen05.ld S(j) -> registers; S free  ----> QK(j+1) -> S(j+1)     (overlaps the exponentials of j)
+//   row max, lazy rescale (rare), exponentials
+//   wait PV(j-1) done (P buffer free); st P(j)       ----> PV(j) -> O            (overlaps the exponentials of j+1)
+//
+// so in steady state a softmax warp never waits for the tensor pipe, and all NT warps of an SM sub-partition keep the
+// XU / FMA pipes busy.
+//
+// Augmented operand layout (PipeCfg::AUG, entry point i2v_fused_self_xframe_aug_fwd): the head dim d = 40 is stored padded
+// to 48, and the spare column kAugCol = 40 does three jobs that otherwise cost FMA-pipe instructions per score:
+//   * Q column 40 = -m (the row's reference max), K column 40 = 1   ->  the QK^T MMA delivers  x = s - m  directly;
+//     the softmax scale * log2(e) is folded into the query projection weights by the caller, so P = 2^x needs no FFMA.
+//     m is an integer that bf16 holds exactly; it is rewritten in the query tile (by the row's own thread, between
+//     two QK MMAs of the tile) only when the lazy-rescale threshold trips, and the one or two S tiles computed with
+//     the previous value take a slow path that subtracts the difference.
+//   * V column 40 = 1   ->  O column 40 = sum_j P_ij, the softmax denominator, accumulated by the PV MMA from exactly
+//     the bf16 P values it multiplies: no FADD chain, no separate row-sum bookkeeping under rescaling.
+// The caller builds these columns for free as zero weight rows plus a bias in the packed QKV projection GEMM.
+//
+// CTA: NT softmax/epilogue warpgroups (one 128-row query tile each, one thread per row), 1 TMA warp, NMW MMA-issuing
+// warps that poll the barriers of their tiles (no tile waits behind another tile's barrier).  One CTA per SM.
+// TMEM columns per tile: S [BN fp32] | P [BN/2: bf16 pairs] | O [DK fp32]; NT * (1.5 BN + DK) <= 512.
+#pragma once
+#include <cuda.h>
+#include "ptx_sm100.cuh"
+#include "dense_attn_sm100.cuh"  // DenseParams / DenseProblem / kRescaleThreshold
+
+namespace i2v {
+
+#ifndef I2V_PARK_NS
+#define I2V_PARK_NS 1000
+#endif
+constexpr uint32_t kParkNs = I2V_PARK_NS;   // suspend-time hint of the producer-side waits
+constexpr int kAugCol = 40;   // augmented layout: head-dim column that carries -max (Q), ones (K, V) and the row sum (O)
+
+template <int DK_, int BLOCK_N_, int NT_, int NSTAGES_, int EMU_, int DEG_ = 3, int NMW_ = 0, bool AUG_ = false>
+struct PipeCfg {
+  static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16
+  static constexpr int BLOCK_N = BLOCK_N_;  // keys per tile
+  static constexpr int NT = NT_;            // query tiles (= softmax warpgroups) per CTA
+  static constexpr int NSTAGES = NSTAGES_;
+  static constexpr int EMU = EMU_;          // of every 8 column pairs, how many take the FMA-pipe exp2
+  static constexpr int DEG = DEG_;
+  static constexpr bool AUG = AUG_;         // augmented operand layout (see the header comment)
+  static constexpr int NMW = NMW_ > 0 ? NMW_ : NT_;   // MMA-issuing warps; warp w serves tiles w, w + NMW, ... by polling
+  static constexpr int THREADS = (4 * NT + 1 + NMW) * 32;
+  static constexpr int KSTEPS = DK / 16;
+  static constexpr int Q_TILE_BYTES = 128 * 128;       // one 64-column swizzle sub-tile (DK <= 64)
+  static constexpr int KV_TILE_BYTES = BLOCK_N * 128;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = NT * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TILE_COLS = BLOCK_N + BLOCK_N / 2 + DK;
+  static constexpr int TMEM_S = 0, TMEM_P = BLOCK_N, TMEM_O = BLOCK_N + BLOCK_N / 2;  // offsets within a tile's columns
+  static_assert(DK % 16 == 0 && DK <= 64, "pipelined kernel: head dim <= 64");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 128, "BLOCK_N");
+  static_assert(NT * TILE_COLS <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+  static_assert(KV_TILE_BYTES % 1024 == 0, "K/V tiles must keep the 1024-byte swizzle-atom alignment");
+  static_assert(THREADS <= 1024, "CTA size");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const __grid_constant__ DenseParams P) {
+  constexpr int DK = Cfg::DK, BN = Cfg::BLOCK_N, NS = Cfg::NSTAGES, KSTEPS = Cfg::KSTEPS, NT = Cfg::NT;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_q = smem;                                  // [NT][128 rows][128 B]
+  uint8_t* sm_k = sm_q + NT * Cfg::Q_TILE_BYTES;         // [NS][BN rows][128 B]
+  uint8_t* sm_v = sm_k + NS * Cfg::KV_TILE_BYTES;        // [NS][BN rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + NS * Cfg::KV_TILE_BYTES);
+  uint64_t* bar_q_full = bars;                        // [1]
+  uint64_t* bar_k_full = bars + 1;                    // [NS]
+  uint64_t* bar_v_full = bars + 1 + NS;               // [NS]
+  uint64_t* bar_kv_empty = bars + 1 + 2 * NS;         // [NS]   one tcgen05.commit per active tile
+  uint64_t* bar_s_full = bars + 1 + 3 * NS;           // [NT]   MMA -> softmax: S(j) written
+  uint64_t* bar_s_free = bar_s_full + NT;             // [NT]   softmax -> MMA: S(j) is in registers (128 arrivals)
+  uint64_t* bar_p_full = bar_s_free + NT;             // [NT]   softmax -> MMA: P(j) stored (128 arrivals)
+  uint64_t* bar_pv_done = bar_p_full + NT;            // [NT]   MMA -> softmax: PV(j) retired (P free, O consistent)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bar_pv_done + NT);
+  static_assert((2 + 3 * NS + 4 * NT) * 8 <= Cfg::BAR_BYTES, "barrier area");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kTmaWarp = 4 * NT, kMmaWarp0 = 4 * NT + 1;
+
+  // work decomposition: q-block fastest so the CTAs sharing one (batch, head) K/V run together (L2 reuse)
+  int x = blockIdx.x;
+  const int qb = x % P.q_blocks;  x /= P.q_blocks;
+  const int h = x % P.heads;      x /= P.heads;
+  const int b = x % P.batch;      x /= P.batch;
+  const DenseProblem& prob = P.prob[x];
+  const int q0 = qb * (128 * NT);
+  const int ntiles = min(NT, (P.sq - q0 + 127) / 128);
+  const int n_kv = (P.skv + BN - 1) / BN;
+  const int bkv = b / prob.kv_group;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(bar_k_full + s, 1);
+      mbar_init(bar_v_full + s, 1);
+      mbar_init(bar_kv_empty + s, ntiles);
+    }
+    for (int t = 0; t < NT; ++t) {
+      mbar_init(bar_s_full + t, 1);
+      mbar_init(bar_s_free + t, 128);
+      mbar_init(bar_p_full + t, 128);
+      mbar_init(bar_pv_done + t, 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp0) tmem_alloc<512>(tmem_base_slot);
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&prob.tm_q);
+    tma_prefetch_desc(&prob.tm_k);
+    tma_prefetch_desc(&prob.tm_v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == kTmaWarp) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q_full, ntiles * Cfg::Q_TILE_BYTES);
+      for (int t = 0; t < ntiles; ++t)
+        tma_load_4d(sm_q + t * Cfg::Q_TILE_BYTES, &prob.tm_q, bar_q_full, 0, h, q0 + t * 128, b, kEvictFirst);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % NS;
+        mbar_wait_parked(bar_kv_empty + s, ((j / NS) & 1) ^ 1, kParkNs);
+        mbar_arrive_expect_tx(bar_k_full + s, Cfg::KV_TILE_BYTES);
+        tma_load_4d(sm_k + s * Cfg::KV_TILE_BYTES, &prob.tm_k, bar_k_full + s, 0, h, j * BN, bkv, kEvictLast);
+        mbar_arrive_expect_tx(bar_v_full + s, Cfg::KV_TILE_BYTES);
+        tma_load_4d(sm_v + s * Cfg::KV_TILE_BYTES, &prob.tm_v, bar_v_full + s, 0, h, j * BN, bkv, kEvictLast);
+      }
+    }
+  } else if (warp >= kMmaWarp0) {
+    // =========================== MMA issuers ===========================
+    // Warp mw serves tiles mw, mw + NMW, ...  Each tile alternates between two steps, QK(j+1) (needs K(j+1) landed and
+    // S(j) read out) and PV(j) (needs V(j) landed and P(j) stored); the warp polls the barriers of its tiles and issues
+    // whichever step is ready, so no tile waits behind another tile's softmax.
+    const int mw = warp - kMmaWarp0;
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, DK, 0, 1);
+    const uint32_t q_addr = smem_u32(sm_q);
+    const uint32_t k_addr = smem_u32(sm_k);
+    const uint32_t v_addr = smem_u32(sm_v);
+    const uint64_t desc_k_major = make_smem_desc_sw128(0, 16, 1024);
+    const uint64_t desc_v = make_smem_desc_sw128(0, Cfg::KV_TILE_BYTES, 1024);
+
+    auto issue_qk = [&](int t, int s) {
+      const uint32_t qa = (q_addr + t * Cfg::Q_TILE_BYTES) >> 4;
+      const uint32_t ka = (k_addr + s * Cfg::KV_TILE_BYTES) >> 4;
+      const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS;
+#pragma unroll
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        const uint64_t da = desc_k_major | (uint64_t)((qa + kk * 2) & 0x3FFF);   // 32 bytes per 16-column k-step
+        const uint64_t db = desc_k_major | (uint64_t)((ka + kk * 2) & 0x3FFF);
+        umma_ss(tm_tile + Cfg::TMEM_S, da, db, idesc_qk, kk > 0 ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int t, int s, bool accumulate) {
+      const uint32_t va = (v_addr + s * Cfg::KV_TILE_BYTES) >> 4;
+      const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS;
+#pragma unroll
+      for (int kk = 0; kk < BN / 16; ++kk) {
+        // B = V tile, MN-major: 16 key rows per k-step (2048 B)
+        const uint64_t db = desc_v | (uint64_t)((va + kk * (2048 >> 4)) & 0x3FFF);
+        umma_ts(tm_tile + Cfg::TMEM_O, tm_tile + Cfg::TMEM_P + kk * 8, db, idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
+      }
+    };
+
+    constexpr int TPM = (NT + Cfg::NMW - 1) / Cfg::NMW;   // tiles per MMA warp
+    int step[TPM];   // per tile: 2*j + 1 = next is QK(j+1) (or nothing when j+1 == n_kv), 2*j + 2 = next is PV(j)
+    int remaining = 0;
+#pragma unroll
+    for (int i = 0; i < TPM; ++i) {
+      step[i] = 1;
+      if (mw + i * Cfg::NMW < ntiles) ++remaining;
+    }
+    if (remaining > 0) {
+      mbar_wait(bar_q_full, 0);
+      mbar_wait(bar_k_full + 0, 0);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < TPM; ++i) {
+          const int t = mw + i * Cfg::NMW;
+          if (t < ntiles) {
+            issue_qk(t, 0);
+            tc_commit(bar_s_full + t);
+          }
+        }
+      }
+      __syncwarp();
+      if (TPM == 1) {
+        // one tile per warp: plain blocking waits, parked in hardware
+        const int t = mw;
+        for (int j = 0; j < n_kv; ++j) {
+          const int s = j % NS;
+          if (j + 1 < n_kv) {
+            const int sn = (j + 1) % NS;
+            mbar_wait_parked(bar_k_full + sn, ((j + 1) / NS) & 1, kParkNs);
+            mbar_wait_parked(bar_s_free + t, j & 1, kParkNs);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_qk(t, sn);
+              tc_commit(bar_s_full + t);
+            }
+            __syncwarp();
+          }
+          mbar_wait_parked(bar_v_full + s, (j / NS) & 1, kParkNs);
+          mbar_wait_parked(bar_p_full + t, j & 1, kParkNs);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(t, s, j > 0);
+            tc_commit(bar_pv_done + t);
+            tc_commit(bar_kv_empty + s);
+          }
+          __syncwarp();
+        }
+        remaining = 0;
+      }
+      long long t_start = clock64();
+      uint32_t idle = 0;
+      while (remaining > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int i = 0; i < TPM; ++i) {
+          const int t = mw + i * Cfg::NMW;
+          if (t >= ntiles || step[i] > 2 * n_kv) continue;
+          const int j = (step[i] - 1) >> 1;
+          if (step[i] & 1) {
+            // QK(j+1)
+            if (j + 1 >= n_kv) { ++step[i]; progressed = true; continue; }
+            const int sn = (j + 1) % NS;
+            if (mbar_try_wait(bar_k_full + sn, ((j + 1) / NS) & 1) && mbar_try_wait(bar_s_free + t, j & 1)) {
+              tc_fence_after();
+              if (elect_one()) {
+                issue_qk(t, sn);
+                tc_commit(bar_s_full + t);
+              }
+              __syncwarp();
+              ++step[i];
+              progressed = true;
+            }
+          } else {
+            // PV(j)
+            const int s = j % NS;
+            if (mbar_try_wait(bar_v_full + s, (j / NS) & 1) && mbar_try_wait(bar_p_full + t, j & 1)) {
+              tc_fence_after();
+              if (elect_one()) {
+                issue_pv(t, s, j > 0);
+                tc_commit(bar_pv_done + t);
+                tc_commit(bar_kv_empty + s);   // K(j) (read by QK(j), issued earlier) and V(j) are released together
+              }
+              __syncwarp();
+              ++step[i];
+              progressed = true;
+              if (step[i] > 2 * n_kv) --remaining;
+            }
+          }
+        }
+        if (!progressed && (++idle & 0xFFFu) == 0 && (clock64() - t_start) > I2V_MBAR_TIMEOUT_CYCLES) __trap();
+      }
+    }
+  } else {
+    // =========================== softmax + epilogue warpgroup of tile t ===========================
+    const int t = warp >> 2;
+    if (t < ntiles) {
+      const int row = (warp & 3) * 32 + lane;      // TMEM lane == query row within the tile
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS + lane_addr;
+      const uint32_t tm_s = tm_tile + Cfg::TMEM_S, tm_p = tm_tile + Cfg::TMEM_P, tm_o = tm_tile + Cfg::TMEM_O;
+      const float c = P.scale_log2e;
+      // plain mode:     m_ref = reference max (integer, log2 domain), l = running row sum
+      // augmented mode: the scores arrive as x = s - m_col (see the header comment); m_ref is where the reference max
+      //                 should be, m_col what the query tile's max column held when the current S tile was computed
+      float m_ref = Cfg::AUG ? 0.f : -INFINITY;
+      float m_col = 0.f;
+      float l = 0.f;
+      bool col_stale = false;   // augmented: m_ref moved, the max column of the query tile must be rewritten
+      // this row's slot in the 128B-swizzled query tile: column kAugCol (16-byte chunk 5) of row `row`
+      uint8_t* q_maxcol = sm_q + t * Cfg::Q_TILE_BYTES + row * 128 + ((((kAugCol * 2) >> 4) ^ (row & 7)) << 4) +
+                          ((kAugCol * 2) & 15);
+
+      auto load_scores = [&](float (&sv)[BN]) {
+        constexpr int N32 = BN / 32, R16 = (BN % 32) / 16;
+#pragma unroll
+        for (int cch = 0; cch < N32; ++cch) {
+          uint32_t r[32];
+          tmem_ld_x32(tm_s + cch * 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[cch * 32 + i] = __uint_as_float(r[i]);
+        }
+        if (R16) {
+          uint32_t r[16];
+          tmem_ld_x16(tm_s + N32 * 32, r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sv[N32 * 32 + i] = __uint_as_float(r[i]);
+        }
+        tc_wait_ld();
+      };
+      auto row_max = [&](const float (&sv)[BN]) -> float {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < BN; i += 8) {
+          mx0 = fmax3(mx0, sv[i + 0], sv[i + 1]);
+          mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+          mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]);
+          mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
+        }
+        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      };
+      // multiply the O accumulator row by alpha; PV(j-1) must have retired and PV(j) is not issued before our p_full
+      auto rescale_o = [&](int j, float alpha) {
+        mbar_wait(bar_pv_done + t, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cch = 0; cch < DK / 16; ++cch) {
+          uint32_t r[16];
+          tmem_ld_x16(tm_o + cch * 16, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_x16(tm_o + cch * 16, r);
+        }
+      };
+      auto store_p = [&](int j, const uint32_t (&pk)[BN / 2]) {
+        if (j > 0) {
+          mbar_wait(bar_pv_done + t, (j - 1) & 1);   // PV(j-1) has finished reading the P columns
+          tc_fence_after();
+        }
+        constexpr int H = BN / 2, N16 = H / 16, R8 = (H % 16) / 8;
+#pragma unroll
+        for (int cch = 0; cch < N16; ++cch) {
+          uint32_t r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = pk[cch * 16 + i];
+          tmem_st_x16(tm_p + cch * 16, r);
+        }
+        if (R8) {
+          uint32_t r[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r[i] = pk[N16 * 16 + i];
+          tmem_st_x8(tm_p + N16 * 16, r);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p_full + t);
+      };
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(bar_s_full + t, j & 1);
+        tc_fence_after();
+        float sv[BN];
+        load_scores(sv);
+        float m_col_next = m_col;
+        if (Cfg::AUG && col_stale) {
+          // QK(j) has retired (we hold its result) and QK(j+1) is not issued before our s_free arrival: the only
+          // window in which the query tile may be touched.  QK(j+1) onwards see the new column.
+          *reinterpret_cast<uint16_t*>(q_maxcol) = (uint16_t)(__float_as_uint(-m_ref) >> 16);   // m_ref is bf16-exact
+          fence_proxy_async_smem();
+          m_col_next = m_ref;
+          col_stale = false;
+        }
+        tc_fence_before();
+        mbar_arrive(bar_s_free + t);   // the MMA warp may overwrite S with QK(j+1) from here on
+
+        const int valid = P.skv - j * BN;
+        const bool full = valid >= BN;
+        if (!full) {  // ragged last tile only (warp-uniform)
+#pragma unroll
+          for (int i = 0; i < BN; ++i)
+            if (i >= valid) sv[i] = -INFINITY;
+        }
+        uint32_t pk[BN / 2];
+        if (!Cfg::AUG) {
+          const float mx = row_max(sv) * c;
+          // lazy rescale: the reference max only moves when a row outgrows it by more than 2^kRescaleThreshold
+          const bool need = mx > m_ref + kRescaleThreshold;   // m_ref = -inf on the first tile
+          if (__any_sync(0xffffffffu, need)) {
+            float alpha = 1.f;
+            if (need) {
+              const float m_new = ceilf(mx);
+              alpha = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new);
+              m_ref = m_new;
+            }
+            if (j > 0) rescale_o(j, alpha);
+            l *= alpha;
+          }
+          if (full) l += softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, true>(sv, c, m_ref, pk);
+          else      l += softmax_exp_row<BN, 0, 3, true>(sv, c, m_ref, pk);   // -inf padding must go through MUFU
+        } else {
+          // sv = s - m_col.  Fast path (nothing moved): P = 2^sv straight away; the row sum comes out of the PV MMA
+          // through the ones column of V.
+          const float mx = row_max(sv) + (m_col - m_ref);   // relative to m_ref
+          const bool need = (j == 0) || mx > kRescaleThreshold;
+          const bool slow = need || (m_col != m_ref) || !full;
+          if (__any_sync(0xffffffffu, slow)) {
+            if (__any_sync(0xffffffffu, need)) {
+              float alpha = 1.f;
+              if (need) {
+                // new reference: an integer >= the row max that bf16 holds exactly (round the magnitude up / down)
+                const float m_int = ceilf(m_ref + mx);
+                const uint32_t mb = __float_as_uint(m_int);
+                const float m_new = __uint_as_float(m_int >= 0.f ? ((mb + 0xFFFFu) & 0xFFFF0000u) : (mb & 0xFFFF0000u));
+                alpha = (j == 0) ? 0.f : ex2_approx(m_ref - m_new);
+                m_ref = m_new;
+                col_stale = true;
+              }
+              if (j > 0) rescale_o(j, alpha);   // scales the row-sum column with the rest of the row
+            }
+            const float delta = m_ref - m_col;   // exact: both are small integers
+#pragma unroll
+            for (int i = 0; i < BN; ++i) sv[i] -= delta;
+            softmax_exp_row<BN, 0, 3, true, true, false>(sv, 1.f, 0.f, pk);
+          } else {
+            softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, true, true, false>(sv, 1.f, 0.f, pk);
+          }
+        }
+        m_col = m_col_next;
+        store_p(j, pk);
+      }
+
+      // ---- epilogue: O / l -> bf16 -> global ----
+      mbar_wait(bar_pv_done + t, (n_kv - 1) & 1);
+      tc_fence_after();
+      const int qrow = q0 + t * 128 + row;
+      __nv_bfloat16* orow = prob.o + (long long)b * prob.o_sb + (long long)qrow * prob.o_ss + (long long)h * prob.o_sh;
+      uint32_t ro[DK / 16][16];
+#pragma unroll
+      for (int cch = 0; cch < DK / 16; ++cch) tmem_ld_x16(tm_o + cch * 16, ro[cch]);
+      tc_wait_ld();
+      if (Cfg::AUG) l = __uint_as_float(ro[kAugCol / 16][kAugCol % 16]);   // sum_j P_ij * 1
+      const float inv_l = 1.f / l;
+      if (qrow < P.sq) {
+#pragma unroll
+        for (int cch = 0; cch < DK / 16; ++cch) {
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const int col = cch * 16 + g8 * 8;
+            if (col < P.d) {  // d is a multiple of 8
+              const uint32_t* r = ro[cch];
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(r[g8 * 8 + 0]) * inv_l, __uint_as_float(r[g8 * 8 + 1]) * inv_l);
+              v.y = pack_bf16x2(__uint_as_float(r[g8 * 8 + 2]) * inv_l, __uint_as_float(r[g8 * 8 + 3]) * inv_l);
+              v.z = pack_bf16x2(__uint_as_float(r[g8 * 8 + 4]) * inv_l, __uint_as_float(r[g8 * 8 + 5]) * inv_l);
+              v.w = pack_bf16x2(__uint_as_float(r[g8 * 8 + 6]) * inv_l, __uint_as_float(r[g8 * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + col) = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace i2v

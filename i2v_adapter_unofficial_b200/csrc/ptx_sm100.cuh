@@ -58,11 +58,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef I2V_MBAR_TIMEOUT_CYCLES
 #define I2V_MBAR_TIMEOUT_CYCLES 4000000000ll
 #endif
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or the hint (ns) expires,
+// instead of burning issue slots of its SM sub-partition in a polling loop (38 % of the executed instructions of the
+// first pipelined build were such polls; the softmax warps share those issue slots).
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // plain polling: measured faster than a long suspend-time hint (the wake-up from a hardware suspend costs more
+  // latency on the softmax <-> MMA hand-offs than the polls cost in issue slots)
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && (clock64() - t0) > I2V_MBAR_TIMEOUT_CYCLES) { __trap(); }
+  }
+}
+
+// Wait that parks the warp in hardware (try_wait with a suspend-time hint) instead of polling: for the producer-side
+// warps (TMA, MMA issue) whose polls would otherwise take issue slots from the softmax warps of their sub-partition.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 2000u) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_suspend(bar, parity, hint_ns)) {
     if ((++spins & 0x3FFu) == 0 && (clock64() - t0) > I2V_MBAR_TIMEOUT_CYCLES) { __trap(); }
   }
 }
@@ -225,6 +254,13 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------------
@@ -311,6 +347,111 @@ __device__ __forceinline__ uint64_t ex2_emulated_pair_noclamp(uint64_t x) {
   const float r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
   const float r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
   return f2_pack(r0, r1);
+}
+
+__device__ __forceinline__ uint64_t f2_fma_rm(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rm.f32x2 %0,%1,%2,%3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+constexpr float kExpMagic = 12582912.f;  // 1.5 * 2^23
+
+// 2^(s*c - m) for a pair of raw scores s with an INTEGER reference max m (log2 domain), FMA / ALU pipes only.
+// k1 = (magic - m, magic - m) is exact because m is an integer, so the Cody-Waite split rides on the scale FMA:
+//   t = fma.rm(s, c, k1)      = magic + floor(x)         x = s*c - m   (one rounding, toward -inf: exact floor)
+//   f = fma.rn(s, c, k1 - t)  = x - floor(x) in [0, 1]   (k1 - t is an exact small integer)
+//   2^f by a minimax polynomial (degree 3: 7.9e-5 / degree 2: 1.7e-3 max relative error; bf16 rounding of P is 2e-3),
+//   2^floor(x) patched into the exponent with an integer shift-add; floor(x) is clamped at -126 on the integer view
+//   of t (positive floats order like integers) so very negative scores give ~0 instead of wrapping.
+// Five packed FMA-pipe instructions per pair (degree 3) + two integer ops per element, against one FFMA2 + two
+// MUFU.EX2 (16 clk of the XU pipe) for the plain path.
+template <int DEG, bool CLAMP>
+__device__ __forceinline__ uint64_t ex2_emu_pair_int(uint64_t s2, uint64_t c2, uint64_t k1) {
+  const uint64_t t = f2_fma_rm(s2, c2, k1);
+  const uint64_t f = f2_fma(s2, c2, f2_sub(k1, t));
+  uint64_t p;
+  if (DEG == 3) {
+    p = f2_fma(f, f2_pack(0.0780693937f, 0.0780693937f), f2_pack(0.2259353543f, 0.2259353543f));
+    p = f2_fma(p, f, f2_pack(0.6959163017f, 0.6959163017f));
+    p = f2_fma(p, f, f2_pack(0.9999210496f, 0.9999210496f));
+  } else {
+    p = f2_fma(f, f2_pack(0.3371894347f, 0.3371894347f), f2_pack(0.6576362757f, 0.6576362757f));
+    p = f2_fma(p, f, f2_pack(1.0017247632f, 1.0017247632f));
+  }
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  int n0 = __float_as_int(t0), n1 = __float_as_int(t1);
+  if (CLAMP) {
+    constexpr int kLo = 0x4B400000 - 126;  // bits of magic - 126
+    n0 = max(n0, kLo);
+    n1 = max(n1, kLo);
+  }
+  const float r0 = __int_as_float(__float_as_int(p0) + (n0 << 23));
+  const float r1 = __int_as_float(__float_as_int(p1) + (n1 << 23));
+  return f2_pack(r0, r1);
+}
+
+// Same for a pair of exponents x that are already final (x = s*c - m was produced by the MMA itself: the scale is
+// folded into the query projection and -m rides in a spare head-dim column, see dense_attn_ring_sm100.cuh):
+//   t = add.rm(x, magic);  f = x - (t - magic)
+template <int DEG, bool CLAMP>
+__device__ __forceinline__ uint64_t ex2_emu_pair_x(uint64_t x2) {
+  const uint64_t mg = f2_pack(kExpMagic, kExpMagic);
+  const uint64_t t = f2_add_rm(x2, mg);
+  const uint64_t f = f2_add(x2, f2_sub(mg, t));
+  uint64_t p;
+  if (DEG == 3) {
+    p = f2_fma(f, f2_pack(0.0780693937f, 0.0780693937f), f2_pack(0.2259353543f, 0.2259353543f));
+    p = f2_fma(p, f, f2_pack(0.6959163017f, 0.6959163017f));
+    p = f2_fma(p, f, f2_pack(0.9999210496f, 0.9999210496f));
+  } else {
+    p = f2_fma(f, f2_pack(0.3371894347f, 0.3371894347f), f2_pack(0.6576362757f, 0.6576362757f));
+    p = f2_fma(p, f, f2_pack(1.0017247632f, 1.0017247632f));
+  }
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  int n0 = __float_as_int(t0), n1 = __float_as_int(t1);
+  if (CLAMP) {
+    constexpr int kLo = 0x4B400000 - 126;
+    n0 = max(n0, kLo);
+    n1 = max(n1, kLo);
+  }
+  const float r0 = __int_as_float(__float_as_int(p0) + (n0 << 23));
+  const float r1 = __int_as_float(__float_as_int(p1) + (n1 << 23));
+  return f2_pack(r0, r1);
+}
+
+// One softmax row step on BN raw scores held in registers: P = 2^(s*c - m) as packed bf16 pairs (pk) + the fp32 row
+// sum.  EMU of every 8 column pairs take the FMA-pipe path; m must be an integer when EMU > 0.
+// PRESCALED: sv already holds x = s*c - m.  SUM = false: the caller gets the row sum elsewhere (ones column of V).
+template <int BN, int EMU, int DEG, bool CLAMP, bool PRESCALED = false, bool SUM = true>
+__device__ __forceinline__ float softmax_exp_row(const float (&sv)[BN], float c, float m, uint32_t (&pk)[BN / 2]) {
+  const uint64_t c2 = f2_pack(c, c);
+  const uint64_t nm2 = f2_pack(-m, -m);
+  const uint64_t k1 = f2_pack(kExpMagic - m, kExpMagic - m);
+  uint64_t ls0 = 0ull, ls1 = 0ull;
+#pragma unroll
+  for (int i = 0; i < BN / 2; ++i) {
+    const uint64_t s2 = f2_pack(sv[2 * i], sv[2 * i + 1]);
+    uint64_t p2;
+    if ((i & 7) < EMU) {
+      p2 = PRESCALED ? ex2_emu_pair_x<DEG, CLAMP>(s2) : ex2_emu_pair_int<DEG, CLAMP>(s2, c2, k1);
+    } else {
+      float x0, x1;
+      f2_unpack(PRESCALED ? s2 : f2_fma(s2, c2, nm2), x0, x1);
+      p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+    }
+    if (SUM) { if (i & 1) ls1 = f2_add(ls1, p2); else ls0 = f2_add(ls0, p2); }
+    float p0, p1;
+    f2_unpack(p2, p0, p1);
+    pk[i] = pack_bf16x2(p0, p1);
+  }
+  float a0, a1;
+  f2_unpack(f2_add(ls0, ls1), a0, a1);
+  return a0 + a1;
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

@@ -109,6 +109,46 @@ def fused_self_xframe(q_self, k_self, v_self, q_x, k_x, v_x, num_frames: int, sc
     return o
 
 
+AUG_D, AUG_DPAD = 40, 48  # the augmented layout exists for SD1.5 level 0 (d = 40 stored padded to 48)
+
+
+def fused_self_xframe_aug(q_self, k_self, v_self, q_x, k_x, v_x, num_frames: int, d: int = AUG_D,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`fused_self_xframe` on the augmented operand layout (include/i2v_attn_b200.h, i2v_fused_self_xframe_aug_fwd).
+
+    All six operands are [.., S, H, 48] views: q[..., :d] pre-multiplied by scale*log2(e) with q[..., d:] = 0,
+    k[..., d] = v[..., d] = 1, k/v[..., d+1:] = 0 (`augment_qkv` builds them from plain tensors; the fused block's
+    packed projection produces them directly).  Returns o [B*F, S, 2, H, d]."""
+    dev = _require_cuda(q_self, k_self, v_self, q_x, k_x, v_x)
+    BF, S, H, dp = q_self.shape
+    if BF % num_frames:
+        raise ValueError(f"Batch size {BF} must be divisible by the number of frames {num_frames}.")
+    o = torch.empty((BF, S, 2, H, d), dtype=q_self.dtype, device=dev) if out is None else out
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_fused_self_xframe_aug_fwd(
+            _desc(q_self), _desc(k_self), _desc(v_self), _desc(o[:, :, 0]), _desc(q_x), _desc(k_x), _desc(v_x),
+            _desc(o[:, :, 1]), BF, H, S, d, dp, num_frames, _dtype_code(q_self), _stream(dev)))
+    return o
+
+
+def augment_qkv(q, k, v, scale: Optional[float] = None):
+    """Plain [.., S, H, 40] q, k, v -> the augmented [.., S, H, 48] operands (test / reference helper: the product
+    path gets this layout from the projection GEMM at no extra pass)."""
+    d = q.shape[-1]
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    pad = AUG_DPAD - d
+
+    def _pad(x, one):
+        z = torch.zeros(*x.shape[:-1], pad, dtype=x.dtype, device=x.device)
+        if one:
+            z[..., 0] = 1
+        return torch.cat([x, z], dim=-1)
+
+    qa = _pad((q.float() * (scale * 1.4426950408889634)).to(q.dtype), False)
+    return qa, _pad(k, True), _pad(v, True)
+
+
 def ip_xattn(q, k, v, n_txt: int, ip_scale: float, kv_group: int = 1, scale: Optional[float] = None,
              mode: int = MODE_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """IP-Adapter decoupled cross-attention.  q [B, Sq, H, d]; k, v [B / kv_group, n_txt + n_ip, H, d] hold the text

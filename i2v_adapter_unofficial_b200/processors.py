@@ -34,7 +34,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from ._lib import MODE_AUTO
+from ._lib import MODE_AUTO, MODE_GENERIC
 
 
 class RuntimeContext:
@@ -83,6 +83,34 @@ def _cat_bias(biases: List[Optional[torch.Tensor]], widths: List[int], like: tor
     if all(b is None for b in biases):
         return None
     return torch.cat([b if b is not None else like.new_zeros(w) for b, w in zip(biases, widths)])
+
+
+_LOG2E = 1.4426950408889634
+
+
+def _augmented_projection(mods, kinds, heads: int, d: int, scale: float):
+    """Weights of a packed projection that emits the augmented operand layout of ``ops.fused_self_xframe_aug``:
+    per part and head ``AUG_DPAD`` output rows -- the ``d`` rows of the module's weight (query parts pre-multiplied by
+    ``scale * log2(e)`` in fp32, then rounded once), zero rows for the padding -- and a bias that is 1 at column ``d``
+    of every key / value head (the ones column) on top of the module's own bias.  ``kinds``: 'q' or 'kv' per part."""
+    dp = ops.AUG_DPAD
+    ws, bs = [], []
+    for m, kind in zip(mods, kinds):
+        w = m.weight.float().view(heads, d, -1)
+        b = m.bias.float().view(heads, d) if m.bias is not None else w.new_zeros(heads, d)
+        if kind == "q":
+            w = w * (scale * _LOG2E)
+            b = b * (scale * _LOG2E)
+        wp = w.new_zeros(heads, dp, w.shape[-1])
+        wp[:, :d] = w
+        bp = w.new_zeros(heads, dp)
+        bp[:, :d] = b
+        if kind == "kv":
+            bp[:, d] = 1.0
+        ws.append(wp.view(heads * dp, -1))
+        bs.append(bp.view(heads * dp))
+    dt = mods[0].weight.dtype
+    return torch.cat(ws).to(dt).contiguous(), torch.cat(bs).to(dt).contiguous()
 
 
 def _check_supported(attn, attention_mask, what: str) -> None:
@@ -182,6 +210,9 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
         self._w_in = _PackedWeights()
         self._w_x = _PackedWeights()
         self._w_out = _PackedWeights()
+        self._w_in_aug = _PackedWeights()
+        self._w_x_aug = _PackedWeights()
+        self.augmented = True  # use the augmented operand layout where the kernel has it (d = 40, bf16)
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
                  scale: float = 1.0, **kwargs):
@@ -215,8 +246,25 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
                                          None if so.bias is None and xo.bias is None else
                                          (so.bias if so.bias is not None else 0) +
                                          (xo.bias if xo.bias is not None else 0)))
-        y = F.linear(x, w_in[0], w_in[1]).view(BF, S, 4, H, d)
         first = x[0::Fr]  # frame 0 of every video: rows b*F (reference :484), no F-times repeat (:485)
+        if (self.augmented and d == ops.AUG_D and x.dtype == torch.bfloat16 and self.mode != MODE_GENERIC
+                and st.first_frame_source is None):
+            # level 0 (d = 40): the projections emit the augmented layout (scale folded into the query weights, ones
+            # column in K and V, head dim padded to 48) that lets the kernel skip the scale FMA and the row-sum adds
+            dp = ops.AUG_DPAD
+            wa = self._w_in_aug.get([m.weight for m in srcs] + [m.bias for m in srcs],
+                                    lambda: _augmented_projection(srcs, ["q", "kv", "kv", "q"], H, d, attn.scale))
+            wxa = self._w_x_aug.get([xa.to_k.weight, xa.to_v.weight, xa.to_k.bias, xa.to_v.bias],
+                                    lambda: _augmented_projection([xa.to_k, xa.to_v], ["kv", "kv"], H, d, attn.scale))
+            y = F.linear(x, wa[0], wa[1]).view(BF, S, 4, H, dp)
+            kvx = F.linear(first, wxa[0], wxa[1]).view(BF // Fr, S, 2, H, dp)
+            o = ops.fused_self_xframe_aug(y[:, :, 0], y[:, :, 1], y[:, :, 2], y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1],
+                                          Fr, d)
+            out = F.linear(o.view(BF, S, 2 * inner), w_out[0], w_out[1])
+            out = attn.to_out[1](out)
+            st.cross_done = True
+            return out
+        y = F.linear(x, w_in[0], w_in[1]).view(BF, S, 4, H, d)
         if st.first_frame_source is not None:  # frame shard: K/V of global frame 0 are broadcast by their owner
             kvx = st.first_frame_source.broadcast_from_first_frame_owner(
                 lambda: F.linear(first, w_x[0], w_x[1]), (BF // Fr, S, 2 * inner), x.dtype, x.device

@@ -82,6 +82,19 @@ int i2v_fused_self_xframe_fwd(const i2v_tensor* q_self, const i2v_tensor* k_self
                               int batch, int heads, int seq, int d, int num_frames, float scale,
                               int dtype, int mode, void* stream);
 
+/* Same operator on the AUGMENTED operand layout, the layout the packed QKV projection of the fused block produces
+ * (processors.py, B200SpatialAttnProcessor): head dim d = 40 stored padded to d_pad = 48 (strides say so), and
+ *   q[..., 0:d] already multiplied by scale * log2(e) (folded into the projection weights), q[..., d:] = 0,
+ *   k[..., d] = 1 and v[..., d] = 1 (a bias of the projection), k/v[..., d+1:] = 0.
+ * The kernel keeps -rowmax in q's column d, so QK^T yields the softmax exponent directly, and reads the softmax
+ * denominator from o's column d.  o_self / o_x receive d columns per head.  bf16 only; any other shape returns
+ * I2V_ERR_UNSUPPORTED (callers then use i2v_fused_self_xframe_fwd). */
+int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_self, const i2v_tensor* v_self,
+                                  const i2v_tensor* o_self, const i2v_tensor* q_x, const i2v_tensor* k_x,
+                                  const i2v_tensor* v_x, const i2v_tensor* o_x,
+                                  int batch, int heads, int seq, int d, int d_pad, int num_frames,
+                                  int dtype, void* stream);
+
 /* IP-Adapter decoupled cross-attention:
  *   o = softmax(scale q k_txt^T) v_txt + ip_scale * softmax(scale q k_ip^T) v_ip
  * k/v tensors hold batch/kv_group entries (text and image tokens are identical for the frames of a video:

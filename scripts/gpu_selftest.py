@@ -252,6 +252,44 @@ def group_tunedense():
     return True
 
 
+def group_tuneaug():
+    """Augmented-layout fused kernel (C2 level-0 shape): variant x exp2-split sweep, error against torch SDPA."""
+    import torch
+    from i2v_adapter_unofficial_b200 import _lib, ops
+
+    torch.manual_seed(3)
+    Bv, Fr, H, S, d = 2, 16, 8, int(os.environ.get("I2V_S", "4096")), 40
+    sc = float(os.environ.get("I2V_QSCALE", "1.0"))
+    q = torch.randn(Bv * Fr, S, H, d, device="cuda", dtype=torch.bfloat16) * sc
+    k = torch.randn(Bv * Fr, S, H, d, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(Bv * Fr, S, H, d, device="cuda", dtype=torch.bfloat16)
+    qx = torch.randn(Bv * Fr, S, H, d, device="cuda", dtype=torch.bfloat16) * sc
+    kx = torch.randn(Bv, S, H, d, device="cuda", dtype=torch.bfloat16)
+    vx = torch.randn(Bv, S, H, d, device="cuda", dtype=torch.bfloat16)
+    qa, ka, va = ops.augment_qkv(q, k, v)
+    qxa, kxa, vxa = ops.augment_qkv(qx, kx, vx)
+    fn = lambda: ops.fused_self_xframe_aug(qa, ka, va, qxa, kxa, vxa, Fr)
+    fl = 2 * 4.0 * Bv * Fr * H * S * S * d
+    ref_self = ref_sdpa(q[:2], k[:2], v[:2])
+    ref_x = ref_sdpa(qx[Fr:Fr + 2], kx[1:2], vx[1:2], kv_group=2)
+    lib = _lib.load()
+    ok = True
+    for variant in [int(a) for a in os.environ.get("I2V_VARIANTS", "4").split(",")]:
+        for emu in [int(a) for a in os.environ.get("I2V_EMUS", "1,3,4,5").split(",")]:
+            lib.i2v_set_tuning(3, variant + 1)
+            lib.i2v_set_tuning(2, emu)
+            ms = _time(fn, iters=5, warm=2)
+            o = fn()
+            e1 = (o[:2, :, 0].float() - ref_self).abs().max().item()
+            e2 = (o[Fr:Fr + 2, :, 1].float() - ref_x).abs().max().item()
+            ok = ok and e1 < 2e-2 and e2 < 2e-2
+            print(f"[tuneaug] variant {variant} emu-key {emu}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s  max_abs_err self {e1:.2e} xframe {e2:.2e}",
+                  flush=True)
+    lib.i2v_set_tuning(3, 0)
+    lib.i2v_set_tuning(2, 0)
+    return ok
+
+
 def group_perftemporal():
     import torch
     from i2v_adapter_unofficial_b200 import ops
@@ -265,7 +303,7 @@ def group_perftemporal():
     return True
 
 
-GROUPS = {"tunedense": group_tunedense, "perfdense": group_perfdense, "perftemporal": group_perftemporal, "generic": group_generic, "temporal": group_temporal, "dense64": group_dense64, "dense": group_dense,
+GROUPS = {"tunedense": group_tunedense, "tuneaug": group_tuneaug, "perfdense": group_perfdense, "perftemporal": group_perftemporal, "generic": group_generic, "temporal": group_temporal, "dense64": group_dense64, "dense": group_dense,
           "fused": group_fused, "ip": group_ip, "perf": group_perf}
 
 

@@ -108,6 +108,61 @@ def test_fused_self_and_cross_frame_matches_oracle(case):
     assert (o[:, :, 1] - _oracle(y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1], Fr)).abs().max().item() <= BF16_TOL
 
 
+def _aug_run(q, k, v, qx, kx, vx, Fr):
+    qa, ka, va = ops.augment_qkv(*_cuda(q, k, v))
+    qxa, kxa, vxa = ops.augment_qkv(*_cuda(qx, kx, vx))
+    return ops.fused_self_xframe_aug(qa, ka, va, qxa, kxa, vxa, Fr).float().cpu()
+
+
+@pytest.mark.parametrize("case", [(2, 4, 8, 256), (1, 16, 8, 1024), (2, 2, 8, 600), (3, 2, 2, 77), (1, 2, 8, 1537)],
+                         ids=lambda c: "V{}F{}H{}S{}".format(*c))
+def test_fused_augmented_layout_matches_oracle(case):
+    # the augmented operand layout (scale folded into q, ones column in k and v, d = 40 padded to 48) is another
+    # encoding of the same operator: same oracle, same tolerance; sizes cover ragged key tiles (S % 64 != 0) and
+    # partially filled query blocks (S % 384 != 0)
+    V, Fr, H, S = case
+    d, BF = 40, V * Fr
+    q, k, v, qx = (_rand((BF, S, H, d), 31 + i) for i in range(4))
+    kx, vx = _rand((V, S, H, d), 41), _rand((V, S, H, d), 42)
+    o = _aug_run(q, k, v, qx, kx, vx, Fr)
+    assert (o[:, :, 0] - _oracle(q, k, v)).abs().max().item() <= BF16_TOL
+    assert (o[:, :, 1] - _oracle(qx, kx, vx, Fr)).abs().max().item() <= BF16_TOL
+
+
+def test_fused_augmented_layout_moving_maximum():
+    # keys whose scores keep growing along the key axis move the reference maximum many times: every move rewrites the
+    # max column of the query tile and sends one or two score tiles through the stale-column slow path
+    V, Fr, H, S, d = 1, 2, 2, 1024, 40
+    q = _rand((V * Fr, S, H, d), 51) * 2
+    ramp = torch.linspace(0.2, 6.0, S).view(1, S, 1, 1)
+    k = (_rand((V * Fr, S, H, d), 52) * ramp).to(torch.bfloat16)
+    kx = (_rand((V, S, H, d), 53) * ramp.flip(1)).to(torch.bfloat16)
+    v, vx = _rand((V * Fr, S, H, d), 54), _rand((V, S, H, d), 55)
+    o = _aug_run(q, k, v, q, kx, vx, Fr)
+    assert torch.isfinite(o).all()
+    # scores reach +-100 octaves here, so the oracle gets the query the kernel sees (the helper rounds q * scale to
+    # bf16 a second time; the product path folds the scale into the projection weights and rounds once)
+    c = d ** -0.5 * 1.4426950408889634
+    q_eff = (ops.augment_qkv(q, k, v)[0][..., :d].float() / c)
+    assert (o[:, :, 0] - _oracle(q_eff, k, v)).abs().max().item() <= BF16_TOL
+    assert (o[:, :, 1] - _oracle(q_eff, kx, vx, Fr)).abs().max().item() <= BF16_TOL
+
+
+def test_fused_augmented_layout_far_below_maximum_scores_vanish():
+    # one dominant key per row and all others > 126 octaves below it: the FMA-pipe exp2 must clamp, not wrap
+    V, Fr, H, S, d = 1, 1, 1, 256, 40
+    q = torch.zeros(1, S, H, d)
+    q[..., 0] = 60.0
+    k = torch.zeros(1, S, H, d)
+    k[:, :, :, 0] = -60.0
+    k[:, 7, :, 0] = 60.0
+    v = _rand((1, S, H, d), 56)
+    qb, kb = q.to(torch.bfloat16), k.to(torch.bfloat16)
+    o = _aug_run(qb, kb, v, qb, kb, v, Fr)
+    assert torch.isfinite(o).all()
+    assert (o[:, :, 0] - v[:, 7:8].float()).abs().max().item() <= BF16_TOL
+
+
 def test_kv_group_indexing_is_bit_identical_to_the_repeated_tensor():
     # reference materialises the first frame F times (einops.repeat, :485); indexing it in place must not change a bit
     V, Fr, H, S, d = 2, 4, 8, 512, 40
