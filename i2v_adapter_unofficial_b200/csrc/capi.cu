@@ -164,8 +164,12 @@ int launch_dense_pipe_cfg(const i2v::DenseParams& Pin, cudaStream_t stream) {
   }
   i2v::DenseParams P = Pin;
   P.q_blocks = (P.sq + 128 * Cfg::NT - 1) / (128 * Cfg::NT);
-  const long long grid = (long long)P.q_blocks * P.heads * P.batch * P.nprob;
-  if (grid <= 0 || grid > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "dense attention grid %lld out of range", grid);
+  const long long items = (long long)P.q_blocks * P.heads * P.batch * P.nprob;
+  if (items <= 0 || items > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "dense attention work items %lld out of range", items);
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const long long grid = items < di->sms ? items : di->sms;   // persistent: one CTA per SM walks the items
   kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -181,9 +185,9 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
   // tiles per CTA, two CTAs per SM; 2 = four 128x64 tiles per CTA, each warpgroup alternating between two
   const int variant = g_tuning[3] > 0 ? g_tuning[3] - 1 : 4;
   // two-segment (IP-Adapter) launches keep all keys in one 128-key tile; at d = 160 that takes the single-query-tile config
-  // variants 3 / 4: software-pipelined kernel (dense_attn_pipe_sm100.cuh), 4 tiles x 48 keys / 3 tiles x 64 keys
+  // variant 4 (default): software-pipelined persistent kernel (dense_attn_pipe_sm100.cuh), 3 query tiles x 64 keys
   const bool pipe = dk == 48 && seg_split < 0 && variant >= 3;
-  const int bn = seg_split >= 0 ? 128 : (pipe ? (variant == 3 ? 48 : 64) : ((dk == 48 && variant >= 1) ? 64 : dense_block_n(dk)));
+  const int bn = seg_split >= 0 ? 128 : ((dk == 48 && variant >= 1) ? 64 : dense_block_n(dk));
   if (seg_split >= 0 && skv > bn)
     return fail(I2V_ERR_UNSUPPORTED, "two-segment softmax needs skv (%d) <= %d", skv, bn);
   i2v::DenseParams P;
@@ -216,14 +220,6 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
     case 16:  return launch_dense_cfg<i2v::DenseCfg<16, 128, 4>>(P, stream);
     case 32:  return launch_dense_cfg<i2v::DenseCfg<32, 128, 4>>(P, stream);
     case 48:
-      if (pipe && variant == 3) {
-        switch (emu) {
-          case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 0, 3, 3>>(P, stream);
-          case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 2, 3, 3>>(P, stream);
-          case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 4, 3, 3>>(P, stream);
-          default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 3, 3, 3>>(P, stream);
-        }
-      }
       if (pipe) {
         switch (emu) {
           case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0>>(P, stream);
@@ -464,8 +460,7 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   DeviceInfo* di = nullptr;
   if ((rc = device_info(&di))) return rc;
   if ((rc = get_encode_fn())) return rc;
-  const int variant = g_tuning[3] > 0 ? g_tuning[3] - 1 : 4;
-  const int bn = variant == 3 ? 48 : 64;
+  const int bn = 64;
   i2v::DenseParams P;
   memset(&P, 0, sizeof(P));
   P.nprob = 2;
@@ -486,20 +481,12 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
     P.prob[i].kv_group = s.kv_group;
   }
   const int emu = g_tuning[2] > 0 ? g_tuning[2] - 1 : -1;
-  if (variant == 3) {
-    switch (emu) {
-      case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 0, 3, 3, true>>(P, (cudaStream_t)stream);
-      case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 2, 3, 3, true>>(P, (cudaStream_t)stream);
-      case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 4, 3, 3, true>>(P, (cudaStream_t)stream);
-      default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 4, 6, 3, 3, 3, true>>(P, (cudaStream_t)stream);
-    }
-  }
   switch (emu) {
-    case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, 0, true>>(P, (cudaStream_t)stream);
-    case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, 0, true>>(P, (cudaStream_t)stream);
-    case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, 0, true>>(P, (cudaStream_t)stream);
-    case 5:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 2, 0, true>>(P, (cudaStream_t)stream);
-    default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, 0, true>>(P, (cudaStream_t)stream);
+    case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, true>>(P, (cudaStream_t)stream);
+    case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true>>(P, (cudaStream_t)stream);
+    case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true>>(P, (cudaStream_t)stream);
+    case 5:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 2, true>>(P, (cudaStream_t)stream);
+    default: return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true>>(P, (cudaStream_t)stream);
   }
 }
 

@@ -26,8 +26,10 @@
 //     the bf16 P values it multiplies: no FADD chain, no separate row-sum bookkeeping under rescaling.
 // The caller builds these columns for free as zero weight rows plus a bias in the packed QKV projection GEMM.
 //
-// CTA: NT softmax/epilogue warpgroups (one 128-row query tile each, one thread per row), 1 TMA warp, NMW MMA-issuing
-// warps that poll the barriers of their tiles (no tile waits behind another tile's barrier).  One CTA per SM.
+// CTA: NT softmax/epilogue warpgroups (one 128-row query tile each, one thread per row), 1 TMA warp, NT MMA-issuing
+// warps (one per tile, so no tile waits behind another tile's barrier; their waits park the warp in hardware).
+// One persistent CTA per SM walks the work items (problem, batch row, head, query block); barrier phases run on
+// across items, so the epilogue of one item overlaps the query load and the first QK^T of the next.
 // TMEM columns per tile: S [BN fp32] | P [BN/2: bf16 pairs] | O [DK fp32]; NT * (1.5 BN + DK) <= 512.
 #pragma once
 #include <cuda.h>
@@ -42,7 +44,7 @@ namespace i2v {
 constexpr uint32_t kParkNs = I2V_PARK_NS;   // suspend-time hint of the producer-side waits
 constexpr int kAugCol = 40;   // augmented layout: head-dim column that carries -max (Q), ones (K, V) and the row sum (O)
 
-template <int DK_, int BLOCK_N_, int NT_, int NSTAGES_, int EMU_, int DEG_ = 3, int NMW_ = 0, bool AUG_ = false>
+template <int DK_, int BLOCK_N_, int NT_, int NSTAGES_, int EMU_, int DEG_ = 3, bool AUG_ = false>
 struct PipeCfg {
   static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16
   static constexpr int BLOCK_N = BLOCK_N_;  // keys per tile
@@ -51,8 +53,7 @@ struct PipeCfg {
   static constexpr int EMU = EMU_;          // of every 8 column pairs, how many take the FMA-pipe exp2
   static constexpr int DEG = DEG_;
   static constexpr bool AUG = AUG_;         // augmented operand layout (see the header comment)
-  static constexpr int NMW = NMW_ > 0 ? NMW_ : NT_;   // MMA-issuing warps; warp w serves tiles w, w + NMW, ... by polling
-  static constexpr int THREADS = (4 * NT + 1 + NMW) * 32;
+  static constexpr int THREADS = (4 * NT + 1 + NT) * 32;   // NT softmax warpgroups, 1 TMA warp, NT MMA warps
   static constexpr int KSTEPS = DK / 16;
   static constexpr int Q_TILE_BYTES = 128 * 128;       // one 64-column swizzle sub-tile (DK <= 64)
   static constexpr int KV_TILE_BYTES = BLOCK_N * 128;
@@ -78,38 +79,47 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
   uint8_t* sm_k = sm_q + NT * Cfg::Q_TILE_BYTES;         // [NS][BN rows][128 B]
   uint8_t* sm_v = sm_k + NS * Cfg::KV_TILE_BYTES;        // [NS][BN rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + NS * Cfg::KV_TILE_BYTES);
-  uint64_t* bar_q_full = bars;                        // [1]
-  uint64_t* bar_k_full = bars + 1;                    // [NS]
-  uint64_t* bar_v_full = bars + 1 + NS;               // [NS]
-  uint64_t* bar_kv_empty = bars + 1 + 2 * NS;         // [NS]   one tcgen05.commit per active tile
-  uint64_t* bar_s_full = bars + 1 + 3 * NS;           // [NT]   MMA -> softmax: S(j) written
+  uint64_t* bar_q_full = bars;                        // [1]    TMA -> MMA: the query tiles of the work item landed
+  uint64_t* bar_q_empty = bars + 1;                   // [1]    MMA -> TMA: every QK of the work item retired (NT arrivals)
+  uint64_t* bar_k_full = bars + 2;                    // [NS]
+  uint64_t* bar_v_full = bars + 2 + NS;               // [NS]
+  uint64_t* bar_kv_empty = bars + 2 + 2 * NS;         // [NS]   one arrival per MMA warp (NT)
+  uint64_t* bar_s_full = bars + 2 + 3 * NS;           // [NT]   MMA -> softmax: S(j) written
   uint64_t* bar_s_free = bar_s_full + NT;             // [NT]   softmax -> MMA: S(j) is in registers (128 arrivals)
   uint64_t* bar_p_full = bar_s_free + NT;             // [NT]   softmax -> MMA: P(j) stored (128 arrivals)
   uint64_t* bar_pv_done = bar_p_full + NT;            // [NT]   MMA -> softmax: PV(j) retired (P free, O consistent)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bar_pv_done + NT);
-  static_assert((2 + 3 * NS + 4 * NT) * 8 <= Cfg::BAR_BYTES, "barrier area");
+  static_assert((3 + 3 * NS + 4 * NT) * 8 <= Cfg::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int kTmaWarp = 4 * NT, kMmaWarp0 = 4 * NT + 1;
 
-  // work decomposition: q-block fastest so the CTAs sharing one (batch, head) K/V run together (L2 reuse)
-  int x = blockIdx.x;
-  const int qb = x % P.q_blocks;  x /= P.q_blocks;
-  const int h = x % P.heads;      x /= P.heads;
-  const int b = x % P.batch;      x /= P.batch;
-  const DenseProblem& prob = P.prob[x];
-  const int q0 = qb * (128 * NT);
-  const int ntiles = min(NT, (P.sq - q0 + 127) / 128);
+  // Persistent CTA: work item = (problem, batch row, head, query block of NT tiles), q-block fastest so the CTAs that
+  // share one (batch, head) K/V run at the same time (L2 reuse).  Every role walks the same item sequence; barrier
+  // phases run on across items, so the epilogue of one item overlaps the query load and the first QK of the next.
+  const int n_items = P.q_blocks * P.heads * P.batch * P.nprob;
   const int n_kv = (P.skv + BN - 1) / BN;
-  const int bkv = b / prob.kv_group;
+  struct Item { const DenseProblem* prob; int h, b, q0, ntiles, bkv; };
+  auto decode = [&](int x) {
+    Item it;
+    const int qb = x % P.q_blocks;  x /= P.q_blocks;
+    it.h = x % P.heads;             x /= P.heads;
+    it.b = x % P.batch;             x /= P.batch;
+    it.prob = &P.prob[x];
+    it.q0 = qb * (128 * NT);
+    it.ntiles = min(NT, (P.sq - it.q0 + 127) / 128);
+    it.bkv = it.b / it.prob->kv_group;
+    return it;
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q_full, 1);
+    mbar_init(bar_q_empty, NT);
     for (int s = 0; s < NS; ++s) {
       mbar_init(bar_k_full + s, 1);
       mbar_init(bar_v_full + s, 1);
-      mbar_init(bar_kv_empty + s, ntiles);
+      mbar_init(bar_kv_empty + s, NT);
     }
     for (int t = 0; t < NT; ++t) {
       mbar_init(bar_s_full + t, 1);
@@ -121,9 +131,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
   }
   if (warp == kMmaWarp0) tmem_alloc<512>(tmem_base_slot);
   if (warp == kTmaWarp && lane == 0) {
-    tma_prefetch_desc(&prob.tm_q);
-    tma_prefetch_desc(&prob.tm_k);
-    tma_prefetch_desc(&prob.tm_v);
+    for (int i = 0; i < P.nprob; ++i) {
+      tma_prefetch_desc(&P.prob[i].tm_q);
+      tma_prefetch_desc(&P.prob[i].tm_k);
+      tma_prefetch_desc(&P.prob[i].tm_v);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -133,36 +145,41 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
   if (warp == kTmaWarp) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_q_full, ntiles * Cfg::Q_TILE_BYTES);
-      for (int t = 0; t < ntiles; ++t)
-        tma_load_4d(sm_q + t * Cfg::Q_TILE_BYTES, &prob.tm_q, bar_q_full, 0, h, q0 + t * 128, b, kEvictFirst);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % NS;
-        mbar_wait_parked(bar_kv_empty + s, ((j / NS) & 1) ^ 1, kParkNs);
-        mbar_arrive_expect_tx(bar_k_full + s, Cfg::KV_TILE_BYTES);
-        tma_load_4d(sm_k + s * Cfg::KV_TILE_BYTES, &prob.tm_k, bar_k_full + s, 0, h, j * BN, bkv, kEvictLast);
-        mbar_arrive_expect_tx(bar_v_full + s, Cfg::KV_TILE_BYTES);
-        tma_load_4d(sm_v + s * Cfg::KV_TILE_BYTES, &prob.tm_v, bar_v_full + s, 0, h, j * BN, bkv, kEvictLast);
+      uint32_t g = 0;   // K/V tiles loaded so far (stage = g % NS)
+      int n = 0;
+      for (int x = blockIdx.x; x < n_items; x += gridDim.x, ++n) {
+        const Item it = decode(x);
+        if (n > 0) mbar_wait_parked(bar_q_empty, (n - 1) & 1, kParkNs);   // the previous item's QK MMAs are done with sm_q
+        mbar_arrive_expect_tx(bar_q_full, it.ntiles * Cfg::Q_TILE_BYTES);
+        for (int t = 0; t < it.ntiles; ++t)
+          tma_load_4d(sm_q + t * Cfg::Q_TILE_BYTES, &it.prob->tm_q, bar_q_full, 0, it.h, it.q0 + t * 128, it.b,
+                      kEvictFirst);
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const int s = g % NS;
+          mbar_wait_parked(bar_kv_empty + s, ((g / NS) & 1) ^ 1, kParkNs);
+          mbar_arrive_expect_tx(bar_k_full + s, Cfg::KV_TILE_BYTES);
+          tma_load_4d(sm_k + s * Cfg::KV_TILE_BYTES, &it.prob->tm_k, bar_k_full + s, 0, it.h, j * BN, it.bkv, kEvictLast);
+          mbar_arrive_expect_tx(bar_v_full + s, Cfg::KV_TILE_BYTES);
+          tma_load_4d(sm_v + s * Cfg::KV_TILE_BYTES, &it.prob->tm_v, bar_v_full + s, 0, it.h, j * BN, it.bkv, kEvictLast);
+        }
       }
     }
   } else if (warp >= kMmaWarp0) {
-    // =========================== MMA issuers ===========================
-    // Warp mw serves tiles mw, mw + NMW, ...  Each tile alternates between two steps, QK(j+1) (needs K(j+1) landed and
-    // S(j) read out) and PV(j) (needs V(j) landed and P(j) stored); the warp polls the barriers of its tiles and issues
-    // whichever step is ready, so no tile waits behind another tile's softmax.
-    const int mw = warp - kMmaWarp0;
+    // =========================== MMA issuer of tile t ===========================
+    // Per KV tile j of its query tile: QK(j+1) as soon as K(j+1) has landed and S(j) has been read out, then PV(j) once
+    // V(j) has landed and P(j) is stored.  The waits park the warp in hardware.
+    const int t = warp - kMmaWarp0;
     constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, DK, 0, 1);
-    const uint32_t q_addr = smem_u32(sm_q);
+    const uint32_t qa = smem_u32(sm_q + t * Cfg::Q_TILE_BYTES) >> 4;
     const uint32_t k_addr = smem_u32(sm_k);
     const uint32_t v_addr = smem_u32(sm_v);
     const uint64_t desc_k_major = make_smem_desc_sw128(0, 16, 1024);
     const uint64_t desc_v = make_smem_desc_sw128(0, Cfg::KV_TILE_BYTES, 1024);
+    const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS;
 
-    auto issue_qk = [&](int t, int s) {
-      const uint32_t qa = (q_addr + t * Cfg::Q_TILE_BYTES) >> 4;
+    auto issue_qk = [&](int s) {
       const uint32_t ka = (k_addr + s * Cfg::KV_TILE_BYTES) >> 4;
-      const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS;
 #pragma unroll
       for (int kk = 0; kk < KSTEPS; ++kk) {
         const uint64_t da = desc_k_major | (uint64_t)((qa + kk * 2) & 0x3FFF);   // 32 bytes per 16-column k-step
@@ -170,9 +187,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
         umma_ss(tm_tile + Cfg::TMEM_S, da, db, idesc_qk, kk > 0 ? 1u : 0u);
       }
     };
-    auto issue_pv = [&](int t, int s, bool accumulate) {
+    auto issue_pv = [&](int s, bool accumulate) {
       const uint32_t va = (v_addr + s * Cfg::KV_TILE_BYTES) >> 4;
-      const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS;
 #pragma unroll
       for (int kk = 0; kk < BN / 16; ++kk) {
         // B = V tile, MN-major: 16 key rows per k-step (2048 B)
@@ -181,109 +197,71 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
       }
     };
 
-    constexpr int TPM = (NT + Cfg::NMW - 1) / Cfg::NMW;   // tiles per MMA warp
-    int step[TPM];   // per tile: 2*j + 1 = next is QK(j+1) (or nothing when j+1 == n_kv), 2*j + 2 = next is PV(j)
-    int remaining = 0;
-#pragma unroll
-    for (int i = 0; i < TPM; ++i) {
-      step[i] = 1;
-      if (mw + i * Cfg::NMW < ntiles) ++remaining;
-    }
-    if (remaining > 0) {
-      mbar_wait(bar_q_full, 0);
-      mbar_wait(bar_k_full + 0, 0);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int i = 0; i < TPM; ++i) {
-          const int t = mw + i * Cfg::NMW;
-          if (t < ntiles) {
-            issue_qk(t, 0);
-            tc_commit(bar_s_full + t);
-          }
-        }
-      }
-      __syncwarp();
-      if (TPM == 1) {
-        // one tile per warp: plain blocking waits, parked in hardware
-        const int t = mw;
-        for (int j = 0; j < n_kv; ++j) {
-          const int s = j % NS;
-          if (j + 1 < n_kv) {
-            const int sn = (j + 1) % NS;
-            mbar_wait_parked(bar_k_full + sn, ((j + 1) / NS) & 1, kParkNs);
-            mbar_wait_parked(bar_s_free + t, j & 1, kParkNs);
-            tc_fence_after();
-            if (elect_one()) {
-              issue_qk(t, sn);
-              tc_commit(bar_s_full + t);
-            }
-            __syncwarp();
-          }
-          mbar_wait_parked(bar_v_full + s, (j / NS) & 1, kParkNs);
-          mbar_wait_parked(bar_p_full + t, j & 1, kParkNs);
+    uint32_t g0 = 0;    // K/V tiles consumed before this item
+    uint32_t it0 = 0;   // KV iterations this tile has run before this item (phase counter of its four barriers)
+    int n = 0;
+    for (int x = blockIdx.x; x < n_items; x += gridDim.x, ++n) {
+      const Item it = decode(x);
+      if (t < it.ntiles) {
+        // QK(jj): needs the query tiles (jj == 0), K(jj), and the S columns read out by the softmax warps
+        auto qk_step = [&](int jj) {
+          const uint32_t g = g0 + jj, itg = it0 + jj;
+          mbar_wait_parked(bar_k_full + g % NS, (g / NS) & 1, kParkNs);
+          if (itg > 0) mbar_wait_parked(bar_s_free + t, (itg - 1) & 1, kParkNs);
           tc_fence_after();
           if (elect_one()) {
-            issue_pv(t, s, j > 0);
+            issue_qk(g % NS);
+            tc_commit(bar_s_full + t);
+          }
+          __syncwarp();
+        };
+        mbar_wait_parked(bar_q_full, n & 1, kParkNs);
+        qk_step(0);
+        for (int j = 0; j < n_kv; ++j) {
+          if (j + 1 < n_kv) qk_step(j + 1);
+          const uint32_t g = g0 + j, itg = it0 + j;
+          const int s = g % NS;
+          mbar_wait_parked(bar_v_full + s, (g / NS) & 1, kParkNs);
+          mbar_wait_parked(bar_p_full + t, itg & 1, kParkNs);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(s, j > 0);
             tc_commit(bar_pv_done + t);
-            tc_commit(bar_kv_empty + s);
+            tc_commit(bar_kv_empty + s);   // K(j) (read by QK(j), issued earlier) and V(j) are released together
+            if (j == n_kv - 1) tc_commit(bar_q_empty);   // every QK of this item precedes this commit
           }
           __syncwarp();
         }
-        remaining = 0;
-      }
-      long long t_start = clock64();
-      uint32_t idle = 0;
-      while (remaining > 0) {
-        bool progressed = false;
-#pragma unroll
-        for (int i = 0; i < TPM; ++i) {
-          const int t = mw + i * Cfg::NMW;
-          if (t >= ntiles || step[i] > 2 * n_kv) continue;
-          const int j = (step[i] - 1) >> 1;
-          if (step[i] & 1) {
-            // QK(j+1)
-            if (j + 1 >= n_kv) { ++step[i]; progressed = true; continue; }
-            const int sn = (j + 1) % NS;
-            if (mbar_try_wait(bar_k_full + sn, ((j + 1) / NS) & 1) && mbar_try_wait(bar_s_free + t, j & 1)) {
-              tc_fence_after();
-              if (elect_one()) {
-                issue_qk(t, sn);
-                tc_commit(bar_s_full + t);
-              }
-              __syncwarp();
-              ++step[i];
-              progressed = true;
-            }
-          } else {
-            // PV(j)
-            const int s = j % NS;
-            if (mbar_try_wait(bar_v_full + s, (j / NS) & 1) && mbar_try_wait(bar_p_full + t, j & 1)) {
-              tc_fence_after();
-              if (elect_one()) {
-                issue_pv(t, s, j > 0);
-                tc_commit(bar_pv_done + t);
-                tc_commit(bar_kv_empty + s);   // K(j) (read by QK(j), issued earlier) and V(j) are released together
-              }
-              __syncwarp();
-              ++step[i];
-              progressed = true;
-              if (step[i] > 2 * n_kv) --remaining;
-            }
-          }
+        it0 += n_kv;
+      } else {
+        // no query tile for this warp in this item (ragged last q-block): keep the shared barriers' arrival counts
+        for (int j = 0; j < n_kv; ++j) {
+          const uint32_t g = g0 + j;
+          mbar_wait_parked(bar_v_full + g % NS, (g / NS) & 1, kParkNs);   // stay in step with the stage ring
+          if (lane == 0) mbar_arrive(bar_kv_empty + g % NS);
         }
-        if (!progressed && (++idle & 0xFFFu) == 0 && (clock64() - t_start) > I2V_MBAR_TIMEOUT_CYCLES) __trap();
+        if (lane == 0) mbar_arrive(bar_q_empty);
+        __syncwarp();
       }
+      g0 += n_kv;
     }
   } else {
     // =========================== softmax + epilogue warpgroup of tile t ===========================
     const int t = warp >> 2;
-    if (t < ntiles) {
-      const int row = (warp & 3) * 32 + lane;      // TMEM lane == query row within the tile
-      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS + lane_addr;
-      const uint32_t tm_s = tm_tile + Cfg::TMEM_S, tm_p = tm_tile + Cfg::TMEM_P, tm_o = tm_tile + Cfg::TMEM_O;
-      const float c = P.scale_log2e;
+    const int row = (warp & 3) * 32 + lane;      // TMEM lane == query row within the tile
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS + lane_addr;
+    const uint32_t tm_s = tm_tile + Cfg::TMEM_S, tm_p = tm_tile + Cfg::TMEM_P, tm_o = tm_tile + Cfg::TMEM_O;
+    const float c = P.scale_log2e;
+    // this row's slot in the 128B-swizzled query tile: column kAugCol (16-byte chunk 5) of row `row`
+    uint8_t* q_maxcol = sm_q + t * Cfg::Q_TILE_BYTES + row * 128 + ((((kAugCol * 2) >> 4) ^ (row & 7)) << 4) +
+                        ((kAugCol * 2) & 15);
+    uint32_t it0 = 0;   // KV iterations this tile has run before this item
+    for (int x = blockIdx.x; x < n_items; x += gridDim.x) {
+      const Item item = decode(x);
+      if (t >= item.ntiles) continue;
+      const DenseProblem& prob = *item.prob;
+      const int h = item.h, b = item.b, q0 = item.q0;
       // plain mode:     m_ref = reference max (integer, log2 domain), l = running row sum
       // augmented mode: the scores arrive as x = s - m_col (see the header comment); m_ref is where the reference max
       //                 should be, m_col what the query tile's max column held when the current S tile was computed
@@ -291,9 +269,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
       float m_col = 0.f;
       float l = 0.f;
       bool col_stale = false;   // augmented: m_ref moved, the max column of the query tile must be rewritten
-      // this row's slot in the 128B-swizzled query tile: column kAugCol (16-byte chunk 5) of row `row`
-      uint8_t* q_maxcol = sm_q + t * Cfg::Q_TILE_BYTES + row * 128 + ((((kAugCol * 2) >> 4) ^ (row & 7)) << 4) +
-                          ((kAugCol * 2) & 15);
 
       auto load_scores = [&](float (&sv)[BN]) {
         constexpr int N32 = BN / 32, R16 = (BN % 32) / 16;
@@ -325,7 +300,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
       };
       // multiply the O accumulator row by alpha; PV(j-1) must have retired and PV(j) is not issued before our p_full
       auto rescale_o = [&](int j, float alpha) {
-        mbar_wait(bar_pv_done + t, (j - 1) & 1);
+        mbar_wait(bar_pv_done + t, (it0 + j - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int cch = 0; cch < DK / 16; ++cch) {
@@ -338,8 +313,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
         }
       };
       auto store_p = [&](int j, const uint32_t (&pk)[BN / 2]) {
-        if (j > 0) {
-          mbar_wait(bar_pv_done + t, (j - 1) & 1);   // PV(j-1) has finished reading the P columns
+        if (j > 0) {   // (j == 0: the epilogue of the previous item already waited for its last PV)
+          mbar_wait(bar_pv_done + t, (it0 + j - 1) & 1);   // PV(j-1) has finished reading the P columns
           tc_fence_after();
         }
         constexpr int H = BN / 2, N16 = H / 16, R8 = (H % 16) / 8;
@@ -362,7 +337,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
       };
 
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(bar_s_full + t, j & 1);
+        mbar_wait(bar_s_full + t, (it0 + j) & 1);
         tc_fence_after();
         float sv[BN];
         load_scores(sv);
@@ -435,8 +410,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
       }
 
       // ---- epilogue: O / l -> bf16 -> global ----
-      mbar_wait(bar_pv_done + t, (n_kv - 1) & 1);
+      mbar_wait(bar_pv_done + t, (it0 + n_kv - 1) & 1);
       tc_fence_after();
+      it0 += n_kv;
       const int qrow = q0 + t * 128 + row;
       __nv_bfloat16* orow = prob.o + (long long)b * prob.o_sb + (long long)qrow * prob.o_ss + (long long)h * prob.o_sh;
       uint32_t ro[DK / 16][16];

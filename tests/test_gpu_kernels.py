@@ -42,6 +42,7 @@ DENSE_CASES = [
     (1, 8, 2304, 2304, 80, 1), (2, 8, 576, 576, 160, 1), (2, 8, 144, 144, 160, 1),
     (2, 8, 200, 77, 40, 1), (3, 2, 1, 1, 40, 1), (2, 4, 129, 257, 64, 1), (4, 8, 256, 256, 40, 2), (6, 2, 300, 300, 16, 3),
     (2, 2, 384, 384, 32, 1), (1, 1, 128, 128, 128, 1),
+    (1, 2, 9216, 9216, 40, 1),   # configs[3]: 96x96 latent, level 0
 ]
 
 
