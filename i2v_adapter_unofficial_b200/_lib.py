@@ -36,6 +36,9 @@ EXPORTED_SYMBOLS = (
     "i2v_gn_stats",
     "i2v_gn_apply_transpose",
     "i2v_untranspose_residual",
+    "i2v_gn_nhwc_scratch_floats",
+    "i2v_gn_nhwc",
+    "i2v_rows_residual",
 )
 
 
@@ -100,6 +103,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_gn_apply_transpose.argtypes = [p, p, p, p, p, i, i, i, i, i, f, p]
     lib.i2v_untranspose_residual.restype = i
     lib.i2v_untranspose_residual.argtypes = [p, p, p, i, i, i, i, p]
+    lib.i2v_gn_nhwc_scratch_floats.restype = ctypes.c_longlong
+    lib.i2v_gn_nhwc_scratch_floats.argtypes = [i, i]
+    lib.i2v_gn_nhwc.restype = i
+    lib.i2v_gn_nhwc.argtypes = [p, p, p, p, p, p, i, i, i, i, i, f, i, i, p]
+    lib.i2v_rows_residual.restype = i
+    lib.i2v_rows_residual.argtypes = [p, p, p, i, i, i, i, p]
 
 
 def load() -> ctypes.CDLL:

@@ -19,6 +19,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+constexpr int kGnMaxChunks = 64;   // row chunks per image of the channels-last GroupNorm statistics pass
 #ifdef I2V_TRACE
 unsigned long long* g_trace = nullptr;
 int g_trace_cta = 0;
@@ -750,6 +751,69 @@ int i2v_untranspose_residual(const void* y, const void* res, void* out, int N, i
   P.N = N; P.C = C; P.S = S; P.fg = fg;
   dim3 grid((S + 63) / 64, C / 64, N);
   i2v::untranspose_residual_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// Channels-last GroupNorm (+ per-(n, c) add, + SiLU, + frame-major -> position-major row permutation), three launches.
+// scratch: at least i2v_gn_nhwc_scratch_floats(N, G) floats.
+long long i2v_gn_nhwc_scratch_floats(int N, int G) { return (long long)N * G * 2 * (kGnMaxChunks + 1); }
+
+int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, void* out, float* scratch, int N, int S,
+                int C, int G, int fg, float eps, int silu, int perm, void* stream) {
+  if (N <= 0 || S <= 0 || C <= 0 || G <= 0 || fg <= 0 || C % G || C % 8 || N % fg)
+    return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc: bad shape N=%d S=%d C=%d G=%d fg=%d", N, S, C, G, fg);
+  if (C / 8 > 512 || G > 256) return fail(I2V_ERR_UNSUPPORTED, "gn_nhwc: C <= 4096 and G <= 256 only (C=%d G=%d)", C, G);
+  if (N > 65535) return fail(I2V_ERR_UNSUPPORTED, "gn_nhwc: N <= 65535 (got %d)", N);
+  if (!x || !w || !b || !out || !scratch) return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc: null pointer");
+  if (!aligned16(x) || !aligned16(out) || (add && !aligned16(add)))
+    return fail(I2V_ERR_MISALIGNED, "gn_nhwc: x/out/add must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  i2v::GnNhwcParams P;
+  P.x = (const __nv_bfloat16*)x; P.out = (__nv_bfloat16*)out; P.add = (const __nv_bfloat16*)add;
+  P.w = (const __nv_bfloat16*)w; P.b = (const __nv_bfloat16*)b;
+  P.N = N; P.S = S; P.C = C; P.G = G; P.fg = fg; P.eps = eps; P.silu = silu; P.perm = perm;
+  int ch = (4 * di->sms + N - 1) / N;   // ~4 CTAs per SM in total
+  if (ch > kGnMaxChunks) ch = kGnMaxChunks;
+  if (ch > (S + 7) / 8) ch = (S + 7) / 8;
+  if (ch < 1) ch = 1;
+  P.rows_per_chunk = (S + ch - 1) / ch;
+  P.CH = (S + P.rows_per_chunk - 1) / P.rows_per_chunk;
+  P.partial = scratch;
+  P.stats = scratch + (long long)N * kGnMaxChunks * G * 2;
+  const int VC = C / 8;
+  const int block = VC > 256 ? (VC + 31) / 32 * 32 : 256;
+  dim3 grid(P.CH, N);
+  i2v::gn_stats_nhwc_kernel<<<grid, block, 2 * C * sizeof(float), (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  const int vg = (N / fg) * G;
+  i2v::gn_finalize_kernel<<<(vg + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  i2v::gn_apply_rows_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(3);
+  return 0;
+}
+
+int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, int C, int fg, void* stream) {
+  if (N <= 0 || S <= 0 || C <= 0 || fg <= 0 || C % 8 || N % fg)
+    return fail(I2V_ERR_BAD_SHAPE, "rows_residual: bad shape N=%d S=%d C=%d fg=%d", N, S, C, fg);
+  if (!y || !res || !out) return fail(I2V_ERR_BAD_SHAPE, "rows_residual: null pointer");
+  if (!aligned16(y) || !aligned16(res) || !aligned16(out))
+    return fail(I2V_ERR_MISALIGNED, "rows_residual: pointers must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  i2v::RowsResidualParams P;
+  P.y = (const __nv_bfloat16*)y; P.res = (const __nv_bfloat16*)res; P.out = (__nv_bfloat16*)out;
+  P.N = N; P.S = S; P.C = C; P.fg = fg;
+  const long long rows = (long long)N * S;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 8LL * di->sms) blocks = 8LL * di->sms;
+  i2v::rows_residual_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -270,4 +270,175 @@ __global__ void __launch_bounds__(256) untranspose_residual_kernel(const Untrans
   *reinterpret_cast<uint4*>(P.out + o0 + P.S) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
 }
 
+// ===============================================================================================================
+// Channels-last (NHWC) GroupNorm family.  With the UNet's convolutions running channels-last (what cuDNN computes in
+// anyway), an activation (N, C, h, w) is stored as [N, S, C] -- which IS the token-major layout the transformer blocks
+// consume, so the spatial wrapper needs no transpose at all and the motion module only a row permutation
+// (frame-major -> position-major rows of C contiguous channels).  Three kernels:
+//   gn_stats_nhwc_kernel     per (n, row chunk): per-group (sum, sum of squares) partials, deterministic
+//   gn_finalize_kernel       per (video, group): reduce chunks and the fg frames that share statistics -> (mean, rstd)
+//   gn_apply_rows_kernel     y = GN(x [+ add[n, c]]) [* sigmoid(.)] with optional row permutation
+// plus rows_residual_kernel for the way back of the motion module (inverse permutation + residual add).
+// `add` is the per-(n, c) time-embedding term of ResnetBlock2D (h + temb[:, :, None, None] before norm2): folding it
+// here removes a full read+write pass.  The reference rounds that sum, the GroupNorm output and the SiLU output to
+// bf16 each (three PyTorch ops); the kernels round at the same places.
+// ===============================================================================================================
+struct GnNhwcParams {
+  const __nv_bfloat16* x;      // [N, S, C]
+  __nv_bfloat16* out;          // [N, S, C] (perm = 0) or [V, S, fg, C] (perm = 1)
+  const __nv_bfloat16* add;    // [N, C] or null
+  float* partial;              // [N, CH, G, 2]
+  float* stats;                // [V, G, 2]  (mean, rstd)
+  const __nv_bfloat16* w;
+  const __nv_bfloat16* b;
+  int N, S, C, G, fg, CH, rows_per_chunk;
+  int silu, perm;
+  float eps;
+};
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const GnNhwcParams P) {
+  extern __shared__ float sm_acc[];   // [2][C]
+  const int chunk = blockIdx.x, n = blockIdx.y;
+  const int VC = P.C / 8;
+  const int rpp = blockDim.x / VC;                  // rows per pass
+  const int tcol = threadIdx.x % VC, trow = threadIdx.x / VC;
+  for (int i = threadIdx.x; i < 2 * P.C; i += blockDim.x) sm_acc[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  float ad[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ad[k] = 0.f;
+  const bool has_add = P.add != nullptr;
+  if (has_add && trow < rpp) {
+    const uint4 a = *reinterpret_cast<const uint4*>(P.add + (long long)n * P.C + tcol * 8);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ad[2 * k] = bf16_lo(aw[k]); ad[2 * k + 1] = bf16_hi(aw[k]); }
+  }
+  const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
+  if (trow < rpp) {
+    const uint4* base = reinterpret_cast<const uint4*>(P.x + (long long)n * P.S * P.C) + tcol;
+    for (int r = r0 + trow; r < r1; r += rpp) {
+      const uint4 v = base[(long long)r * VC];
+      const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a = bf16_lo(ww[k]), b = bf16_hi(ww[k]);
+        if (has_add) { a = bf16_round(a + ad[2 * k]); b = bf16_round(b + ad[2 * k + 1]); }
+        s[2 * k] += a; q[2 * k] += a * a;
+        s[2 * k + 1] += b; q[2 * k + 1] += b * b;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sm_acc[tcol * 8 + k], s[k]);
+      atomicAdd(&sm_acc[P.C + tcol * 8 + k], q[k]);
+    }
+  }
+  __syncthreads();
+  // NOTE: shared-memory float atomics make the per-channel sums order-dependent in the last bits; the reduction
+  // over channels, chunks and frames below is in a fixed order.
+  const int cg = P.C / P.G;
+  if (threadIdx.x < P.G) {
+    float a = 0.f, b = 0.f;
+    for (int c = threadIdx.x * cg; c < (threadIdx.x + 1) * cg; ++c) { a += sm_acc[c]; b += sm_acc[P.C + c]; }
+    float* o = P.partial + (((long long)n * P.CH + chunk) * P.G + threadIdx.x) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+__global__ void gn_finalize_kernel(const GnNhwcParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (v, g)
+  const int V = P.N / P.fg;
+  if (i >= V * P.G) return;
+  const int v = i / P.G, g = i - v * P.G;
+  float a = 0.f, b = 0.f;
+  for (int f = 0; f < P.fg; ++f)
+    for (int ch = 0; ch < P.CH; ++ch) {
+      const float* pp = P.partial + ((((long long)v * P.fg + f) * P.CH + ch) * P.G + g) * 2;
+      a += pp[0]; b += pp[1];
+    }
+  const float cnt = (float)P.fg * (float)(P.C / P.G) * (float)P.S;
+  const float mean = a / cnt;
+  P.stats[2 * i] = mean;
+  P.stats[2 * i + 1] = rsqrtf(fmaxf(b / cnt - mean * mean, 0.f) + P.eps);
+}
+
+__global__ void __launch_bounds__(256) gn_apply_rows_kernel(const GnNhwcParams P) {
+  extern __shared__ float sm_tab[];   // A[C], B[C], T[C]:  y = (x + T) * A + B
+  const int chunk = blockIdx.x, n = blockIdx.y;
+  const int v = n / P.fg, f = n - v * P.fg;
+  const int cg = P.C / P.G;
+  for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
+    const float mean = P.stats[2 * (v * P.G + c / cg)], rstd = P.stats[2 * (v * P.G + c / cg) + 1];
+    const float a = rstd * __bfloat162float(P.w[c]);
+    sm_tab[c] = a;
+    sm_tab[P.C + c] = __bfloat162float(P.b[c]) - mean * a;
+    sm_tab[2 * P.C + c] = P.add ? __bfloat162float(P.add[(long long)n * P.C + c]) : 0.f;
+  }
+  __syncthreads();
+  const int VC = P.C / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
+  const bool has_add = P.add != nullptr;
+  for (int r = r0 + warp; r < r1; r += nwarps) {
+    const uint4* src = reinterpret_cast<const uint4*>(P.x + ((long long)n * P.S + r) * P.C);
+    const long long orow = P.perm ? (((long long)v * P.S + r) * P.fg + f) : ((long long)n * P.S + r);
+    uint4* dst = reinterpret_cast<uint4*>(P.out + orow * P.C);
+    for (int cv = lane; cv < VC; cv += 32) {
+      const uint4 xv = src[cv];
+      const uint32_t ww[4] = {xv.x, xv.y, xv.z, xv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = cv * 8 + 2 * k;
+        float a = bf16_lo(ww[k]), b = bf16_hi(ww[k]);
+        if (has_add) { a = bf16_round(a + sm_tab[2 * P.C + c]); b = bf16_round(b + sm_tab[2 * P.C + c + 1]); }
+        a = fmaf(a, sm_tab[c], sm_tab[P.C + c]);
+        b = fmaf(b, sm_tab[c + 1], sm_tab[P.C + c + 1]);
+        if (P.silu) {
+          a = bf16_round(a); b = bf16_round(b);
+          a = a / (1.f + __expf(-a));
+          b = b / (1.f + __expf(-b));
+        }
+        o[k] = bf16_pack(a, b);
+      }
+      dst[cv] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// out[n, s, :] = y[(v*S + s) * fg + f, :] + res[n, s, :]      (n = v * fg + f; fg = 1: plain row-wise add)
+struct RowsResidualParams {
+  const __nv_bfloat16* y;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* out;
+  int N, S, C, fg;
+};
+
+__global__ void __launch_bounds__(256) rows_residual_kernel(const RowsResidualParams P) {
+  const int VC = P.C / 8;
+  const long long rows = (long long)P.N * P.S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (long long row = (long long)blockIdx.x * nwarps + warp; row < rows; row += (long long)gridDim.x * nwarps) {
+    const int n = (int)(row / P.S), s = (int)(row - (long long)n * P.S);
+    const int v = n / P.fg, f = n - v * P.fg;
+    const uint4* ysrc = reinterpret_cast<const uint4*>(P.y + (((long long)v * P.S + s) * P.fg + f) * P.C);
+    const uint4* rsrc = reinterpret_cast<const uint4*>(P.res + row * P.C);
+    uint4* dst = reinterpret_cast<uint4*>(P.out + row * P.C);
+    for (int cv = lane; cv < VC; cv += 32) {
+      const uint4 a = ysrc[cv], b = rsrc[cv];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = bf16_pack(bf16_lo(aw[k]) + bf16_lo(bw[k]), bf16_hi(aw[k]) + bf16_hi(bw[k]));
+      dst[cv] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 }  // namespace i2v

@@ -152,6 +152,14 @@ def _layout_ok(x: torch.Tensor, norm: nn.GroupNorm) -> bool:
     return C % 64 == 0 and (h * w) % 8 == 0 and C % G == 0 and (C // G) % 2 == 0 and x.shape[0] <= 65535
 
 
+def _nhwc_ok(x: torch.Tensor, norm: nn.GroupNorm) -> bool:
+    """Channels-last activation the NHWC GroupNorm kernels take."""
+    if not (ops.is_channels_last(x) and isinstance(norm, nn.GroupNorm) and norm.affine):
+        return False
+    C, G = x.shape[1], norm.num_groups
+    return C % 8 == 0 and C % G == 0 and C <= 4096 and x.shape[0] <= 65535 and not x.is_contiguous()
+
+
 def _make_transformer2d_forward(module: nn.Module, original: Callable):
     @functools.wraps(original)
     def forward(hidden_states, *args, **kwargs):
@@ -165,14 +173,22 @@ def _make_transformer2d_forward(module: nn.Module, original: Callable):
                   and bound.get("attention_mask") is None and bound.get("encoder_attention_mask") is None
                   and len(args) <= len(names) and set(kwargs) <= set(names) and (conv_proj or lin_proj)
                   and module.proj_out.weight.shape[0] == hidden_states.shape[1])
-        if not simple:
+        nhwc = (_fast_ok(hidden_states, module) and _nhwc_ok(hidden_states, module.norm)
+                and bound.get("attention_mask") is None and bound.get("encoder_attention_mask") is None
+                and len(args) <= len(names) and set(kwargs) <= set(names) and (conv_proj or lin_proj)
+                and module.proj_out.weight.shape[0] == hidden_states.shape[1])
+        if not simple and not nhwc:
             return original(hidden_states, *args, **kwargs)
         N, C, h, w = hidden_states.shape
         norm = module.norm
         # :218-234  GroupNorm(32, eps 1e-6) -> proj_in -> (BF, S, inner), without the NCHW intermediate
-        tokens = ops.group_norm_tokens(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, 1)
+        if nhwc:   # channels-last activation == token-major already: no transpose either way
+            tokens = ops.group_norm_nhwc(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, 1)
+            tokens = tokens.permute(0, 2, 3, 1).reshape(N, h * w, C)
+        else:
+            tokens = ops.group_norm_tokens(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, 1)
         inner = module.proj_in.weight.shape[0]
-        tokens = F.linear(tokens, module.proj_in.weight.view(inner, C), module.proj_in.bias)
+        tokens = F.linear(tokens, module.proj_in.weight.reshape(inner, C), module.proj_in.bias)
         for block in module.transformer_blocks:                                                  # :244-296
             tokens = block(tokens, enable_cross_frame_attn=bound.get("enable_cross_frame_attn", False),
                            num_frames=bound.get("num_frames"), attention_mask=None,
@@ -180,8 +196,12 @@ def _make_transformer2d_forward(module: nn.Module, original: Callable):
                            timestep=bound.get("timestep"), cross_attention_kwargs=bound.get("cross_attention_kwargs"),
                            class_labels=bound.get("class_labels"))
         # :298-314  proj_out -> (BF, C, h, w) -> + residual
-        tokens = F.linear(tokens, module.proj_out.weight.view(C, inner), module.proj_out.bias)
-        output = ops.tokens_to_nchw_residual(tokens.contiguous(), hidden_states, 1)
+        tokens = F.linear(tokens, module.proj_out.weight.reshape(C, inner), module.proj_out.bias)
+        if nhwc:
+            tokens += hidden_states.permute(0, 2, 3, 1).reshape(N, h * w, C)
+            output = tokens.view(N, h, w, C).permute(0, 3, 1, 2)   # a channels-last (N, C, h, w) tensor, no copy
+        else:
+            output = ops.tokens_to_nchw_residual(tokens.contiguous(), hidden_states, 1)
         if not bound.get("return_dict", True):
             return (output,)
         return _Sample(output)
@@ -198,22 +218,70 @@ def _make_temporal_forward(module: nn.Module, original: Callable):
                 cross_attention_kwargs=None, return_dict: bool = True):
         simple = (_fast_ok(hidden_states, module) and _layout_ok(hidden_states, module.norm)
                   and hidden_states.shape[0] % max(num_frames, 1) == 0 and isinstance(module.proj_in, nn.Linear))
-        if not simple:
+        nhwc = (_fast_ok(hidden_states, module) and _nhwc_ok(hidden_states, module.norm)
+                and hidden_states.shape[0] % max(num_frames, 1) == 0 and isinstance(module.proj_in, nn.Linear))
+        if not simple and not nhwc:
             return original(hidden_states, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
                             class_labels=class_labels, num_frames=num_frames,
                             cross_attention_kwargs=cross_attention_kwargs, return_dict=return_dict)
         norm = module.norm
         # GroupNorm over (C/G, F, h, w) per video, then (BF, C, h, w) -> (B*S, F, C) in the same pass
-        x = ops.group_norm_tokens(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, num_frames)
+        if nhwc:
+            x = ops.group_norm_nhwc(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, num_frames,
+                                    to_positions=True)
+        else:
+            x = ops.group_norm_tokens(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, num_frames)
         x = module.proj_in(x)
         for block in module.transformer_blocks:
             x = block(x, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
                       cross_attention_kwargs=cross_attention_kwargs, class_labels=class_labels)
         x = module.proj_out(x)
-        output = ops.tokens_to_nchw_residual(x.contiguous(), hidden_states, num_frames)
+        if nhwc:
+            output = ops.positions_to_nhwc_residual(x.contiguous(), hidden_states, num_frames)
+        else:
+            output = ops.tokens_to_nchw_residual(x.contiguous(), hidden_states, num_frames)
         if not return_dict:
             return (output,)
         return _Sample(output)
+
+    return forward
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ResnetBlock2D in channels-last: only its two GroupNorm + SiLU prologues (and the time-embedding add) move into the
+# library; the convolutions stay PyTorch / cuDNN calls (north_star), now fed the layout cuDNN computes in.
+# ----------------------------------------------------------------------------------------------------------------
+def _is_silu(fn) -> bool:
+    return isinstance(fn, nn.SiLU) or fn is F.silu
+
+
+def _make_resnet_forward(module: nn.Module, original: Callable):
+    @functools.wraps(original)
+    def forward(x, temb=None, *args, **kwargs):
+        simple = (_fast_ok(x, module) and temb is not None and _nhwc_ok(x, module.norm1)
+                  and isinstance(module.norm2, nn.GroupNorm) and module.norm2.affine
+                  and _is_silu(getattr(module, "nonlinearity", None))
+                  and getattr(module, "time_emb_proj", None) is not None
+                  and getattr(module, "time_embedding_norm", "default") in (None, "default")
+                  and not getattr(module, "up", False) and not getattr(module, "down", False)
+                  and getattr(module, "upsample", None) is None and getattr(module, "downsample", None) is None
+                  and getattr(module.dropout, "p", 0.0) == 0.0 and module.conv1.out_channels % 8 == 0
+                  and module.conv1.out_channels <= 4096)
+        if not simple:
+            return original(x, temb, *args, **kwargs)
+        n1, n2 = module.norm1, module.norm2
+        h = ops.group_norm_nhwc(x, n1.weight, n1.bias, n1.num_groups, n1.eps, 1, silu=True)
+        h = module.conv1(h)
+        t = module.time_emb_proj(F.silu(temb))
+        if not ops.is_channels_last(h):
+            h = h.contiguous(memory_format=torch.channels_last)
+        h = ops.group_norm_nhwc(h, n2.weight, n2.bias, n2.num_groups, n2.eps, 1, silu=True, add=t)
+        h = module.conv2(h)
+        if getattr(module, "conv_shortcut", None) is not None:
+            x = module.conv_shortcut(x)
+        out = x + h
+        osf = getattr(module, "output_scale_factor", 1.0)
+        return out if osf == 1.0 else out / osf
 
     return forward
 
@@ -258,4 +326,6 @@ def install_fast_forwards(root: nn.Module) -> List[Callable[[], None]]:
             patch(module, _make_transformer2d_forward(module, module.forward))
         elif name == "TransformerTemporalModel":
             patch(module, _make_temporal_forward(module, module.forward))
+        elif name == "ResnetBlock2D":
+            patch(module, _make_resnet_forward(module, module.forward))
     return undo

@@ -297,6 +297,53 @@ def tokens_to_nchw_residual(y: torch.Tensor, residual: torch.Tensor, frames_per_
     return out
 
 
+def is_channels_last(x: torch.Tensor) -> bool:
+    """(N, C, h, w) stored as [N, h, w, C] (torch.channels_last), dense."""
+    return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+
+
+def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, eps: float,
+                    frames_per_stat: int = 1, silu: bool = False, add: Optional[torch.Tensor] = None,
+                    to_positions: bool = False) -> torch.Tensor:
+    """GroupNorm of a channels-last activation x (N, C, h, w) [+ per-(n, c) ``add`` before, + SiLU after].
+
+    Returns a channels-last (N, C, h, w) tensor, or with ``to_positions`` the motion module's [N/F * h*w, F, C]
+    token layout (statistics shared by the F = ``frames_per_stat`` frames of a video either way)."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and is_channels_last(x)):
+        raise RuntimeError("group_norm_nhwc: needs a CUDA bf16 channels-last tensor (no CPU fallback)")
+    dev = x.device
+    N, C, h, w = x.shape
+    S, fg = h * w, frames_per_stat
+    lib = _lib.load()
+    scratch = torch.empty((int(lib.i2v_gn_nhwc_scratch_floats(N, groups)),), dtype=torch.float32, device=dev)
+    if to_positions:
+        out = torch.empty((N // fg * S, fg, C), dtype=x.dtype, device=dev)
+    else:
+        out = torch.empty_like(x)  # preserves channels_last
+    if add is not None:
+        add = add.to(dtype=x.dtype).reshape(N, C).contiguous()
+    with _on_device(dev):
+        _lib.check(lib.i2v_gn_nhwc(x.data_ptr(), add.data_ptr() if add is not None else None, weight.data_ptr(),
+                                   bias.data_ptr(), out.data_ptr(), scratch.data_ptr(), N, S, C, groups, fg, float(eps),
+                                   int(silu), int(to_positions), _stream(dev)))
+    return out
+
+
+def positions_to_nhwc_residual(y: torch.Tensor, residual: torch.Tensor, frames_per_stat: int) -> torch.Tensor:
+    """Motion module, way back: y [N/F * h*w, F, C] + channels-last residual (N, C, h, w) -> channels-last (N, C, h, w)."""
+    if not (y.is_cuda and y.dtype == torch.bfloat16 and y.is_contiguous() and is_channels_last(residual)):
+        raise RuntimeError("positions_to_nhwc_residual: needs CUDA bf16 tensors, residual channels-last (no CPU fallback)")
+    N, C, h, w = residual.shape
+    if y.numel() != residual.numel():
+        raise ValueError(f"y {tuple(y.shape)} and residual {tuple(residual.shape)} differ in size")
+    out = torch.empty_like(residual)
+    lib = _lib.load()
+    with _on_device(y.device):
+        _lib.check(lib.i2v_rows_residual(y.data_ptr(), residual.data_ptr(), out.data_ptr(), N, h * w, C, frames_per_stat,
+                                         _stream(y.device)))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 # torch.library registration: torch.ops.i2v_b200.*  (CUDA key only -> CPU tensors raise NotImplementedError)
 # ----------------------------------------------------------------------------------------------------------

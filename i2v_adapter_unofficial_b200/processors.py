@@ -483,7 +483,7 @@ def _bind_forward_args(module: nn.Module, args: Tuple, kwargs: Dict[str, Any]) -
 
 
 def install(unet: nn.Module, mode: int = MODE_AUTO, fuse_cross_frame: bool = True,
-            fast_path: bool = True) -> Installation:
+            fast_path: bool = True, channels_last: bool = True) -> Installation:
     """Swap every attention processor of ``unet`` (a ``UNetMotionCrossFrameAttnModel`` — the reference's or
     ``hostmodel``'s — or any sub-module exposing ``attn_processors`` / ``set_attn_processor``) for the B200 ones.
 
@@ -556,8 +556,22 @@ def install(unet: nn.Module, mode: int = MODE_AUTO, fuse_cross_frame: bool = Tru
 
     apply_attn_processors(unet, new)
     undo_forwards = []
+    if fast_path and channels_last and any(p.is_cuda and p.dtype == torch.bfloat16 for p in unet.parameters()):
+        # Convolution weights to channels-last: the activations then flow through the UNet as [N, h, w, C], which is
+        # both what cuDNN computes in (its NCHW <-> NHWC conversion kernels disappear) and the token-major layout of
+        # the transformer blocks (the spatial wrapper's layout changes disappear, the motion module's become a row
+        # permutation).  Values, state-dict keys and shapes are untouched; only strides of 4-D parameters change.
+        converted = [p for p in unet.parameters()
+                     if p.dim() == 4 and not p.is_contiguous(memory_format=torch.channels_last)]
+        unet.to(memory_format=torch.channels_last)
+
+        def restore_format(params=converted):   # uninstall gives the stock path back bit for bit
+            for p in params:
+                p.data = p.data.contiguous()
+
+        undo_forwards.append(restore_format)
     if fast_path:
         from .fastpath import install_fast_forwards
 
-        undo_forwards = install_fast_forwards(unet)
+        undo_forwards = undo_forwards + install_fast_forwards(unet)
     return Installation(unet, previous, hooks, context, new, undo_forwards)

@@ -149,6 +149,23 @@ int i2v_gn_apply_transpose(const void* x, const float* partial, const void* w, c
                            int S, int G, int fg, float eps, void* stream);
 int i2v_untranspose_residual(const void* y, const void* res, void* out, int N, int C, int S, int fg, void* stream);
 
+/* Channels-last (NHWC) GroupNorm family: x is [N, S, C] bf16, i.e. an (N, C, h, w) activation in
+ * torch.channels_last -- the format the reference's convolutions run in on the GPU and, at the same time, the
+ * token-major layout of the transformer blocks.
+ *   out = GroupNorm_G(x + add[n, c]) * w + b, optionally followed by SiLU (silu = 1);
+ * statistics are shared by the fg consecutive images of a video (fg = 1: nn.GroupNorm on (N, C, h, w), reference
+ * src/modules/i2v_adapter.py:218 and the ResnetBlock2D norms; fg = num_frames: the motion module's GroupNorm over
+ * (B, C, F, h, w)).  add (may be NULL) is ResnetBlock2D's time-embedding term added before norm2.
+ * perm = 0: out rows keep x's order; perm = 1: out is [N/fg, S, fg, C] (position-major rows for the motion module).
+ * scratch: i2v_gn_nhwc_scratch_floats(N, G) floats of device memory. */
+long long i2v_gn_nhwc_scratch_floats(int N, int G);
+int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, void* out, float* scratch,
+                int N, int S, int C, int G, int fg, float eps, int silu, int perm, void* stream);
+
+/* out[n, s, :] = y[(v*S + s)*fg + f, :] + res[n, s, :] with n = v*fg + f: the motion module's way back to the
+ * frame-major channels-last activation, fused with its residual add. */
+int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, int C, int fg, void* stream);
+
 /* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
  * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),
  * key 3: dense-attention tile variant + 1 for head dims <= 48 (see capi.cu). */

@@ -155,3 +155,85 @@ def test_unet_fast_path_equals_processor_only_path():
     cos = {k: F.cosine_similarity(v.flatten(), ref.flatten(), dim=0).item() for k, v in outs.items()}
     assert cos[True] >= 0.999 and cos[False] >= 0.999, cos
     assert cos[True] >= cos[False] - 2e-4
+
+
+# ---- channels-last (NHWC) GroupNorm family ----------------------------------------------------------------------
+def _gn_ref(x, w, b, G, eps, fg, add=None, silu=False):
+    """fp32 restatement on the bf16 inputs with the reference's rounding points (each PyTorch op rounds to bf16)."""
+    xf = x.float()
+    if add is not None:
+        xf = (xf + add.float()[:, :, None, None]).to(torch.bfloat16).float()
+    N, C, h, w_ = xf.shape
+    V = N // fg
+    y = xf.view(V, fg, C, h, w_).permute(0, 2, 1, 3, 4)                       # (V, C, F, h, w): statistics per video
+    y = F.group_norm(y, G, w.float(), b.float(), eps).permute(0, 2, 1, 3, 4).reshape(N, C, h, w_)
+    if silu:
+        y = F.silu(y.to(torch.bfloat16).float())
+    return y
+
+
+@pytest.mark.parametrize("case", [(4, 320, 16, 16, 32, 1), (6, 640, 8, 8, 32, 3), (2, 2560, 8, 8, 32, 1),
+                                  (2, 1920, 4, 4, 32, 2), (3, 64, 5, 7, 8, 1), (32, 320, 32, 32, 32, 16)],
+                         ids=lambda c: "N{}C{}h{}w{}G{}fg{}".format(*c))
+@pytest.mark.parametrize("variant", ["plain", "silu", "add_silu"])
+def test_group_norm_nhwc(case, variant):
+    N, C, h, w_, G, fg = case
+    x = _rand((N, C, h, w_), 3, 1.5, 0.3)
+    wt, bs = _rand((C,), 4, 0.2, 1.0), _rand((C,), 5, 0.3)
+    add = _rand((N, C), 6, 0.7) if variant == "add_silu" else None
+    silu = variant != "plain"
+    ref = _gn_ref(x, wt, bs, G, 1e-6, fg, add, silu)
+    xc = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    y = ops.group_norm_nhwc(xc, wt.to(DEV), bs.to(DEV), G, 1e-6, fg, silu=silu,
+                            add=None if add is None else add.to(DEV))
+    assert ops.is_channels_last(y) or h * w_ == 1
+    assert (y.float().cpu() - ref).abs().max().item() <= 4e-2
+    if variant == "plain":
+        # motion-module layout: [V*S, F, C] with row (v*S + s)*F + f
+        yp = ops.group_norm_nhwc(xc, wt.to(DEV), bs.to(DEV), G, 1e-6, fg, to_positions=True)
+        V, S = N // fg, h * w_
+        want = ref.view(V, fg, C, S).permute(0, 3, 1, 2).reshape(V * S, fg, C)
+        assert (yp.float().cpu() - want).abs().max().item() <= 4e-2
+        # and back, with the residual
+        res = _rand((N, C, h, w_), 7)
+        back = ops.positions_to_nhwc_residual(yp, res.to(DEV).contiguous(memory_format=torch.channels_last), fg)
+        assert ops.is_channels_last(back) or h * w_ == 1
+        want_back = yp.float().cpu().view(V, S, fg, C).permute(0, 2, 3, 1).reshape(N, C, h, w_) + res.float()
+        assert (back.float().cpu() - want_back).abs().max().item() <= 2e-2
+
+
+def test_nhwc_kernels_reject_what_they_do_not_support():
+    x = torch.zeros(2, 64, 4, 4, device=DEV, dtype=torch.bfloat16)
+    w = torch.ones(64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="channels-last"):
+        ops.group_norm_nhwc(x, w, w, 8, 1e-5)                       # NCHW-contiguous input
+    xc = x.contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError, match="bad shape"):
+        ops.group_norm_nhwc(xc, w, w, 7, 1e-5)                      # C % G != 0
+
+
+def test_unet_channels_last_equals_nchw_fast_path():
+    """Whole UNet, bf16: the channels-last data flow (default) against the NCHW fast path and the fp32 oracle."""
+    from oracle.unet_oracle import unet_oracle
+
+    unet = randomize_zero_init(make_unet(SD15_HEADDIM_CFG, ip_adapter=True))
+    sample, ctx, img = unet_inputs(unet, videos=1, frames=4, size=32, tokens=77, image_embed_dim=64)
+    with torch.no_grad():
+        ref = unet_oracle(dict(unet.state_dict()), dict(unet.config), sample, 37, True, ctx, img)
+    outs = {}
+    for cl in (False, True):
+        u = randomize_zero_init(make_unet(SD15_HEADDIM_CFG, ip_adapter=True))
+        u.load_state_dict(unet.state_dict())
+        u = u.to(DEV, torch.bfloat16)
+        handle = install(u, channels_last=cl)
+        n0 = _lib.launch_count()
+        with torch.no_grad():
+            outs[cl] = u(sample.to(DEV, torch.bfloat16), 37, True, ctx.to(DEV, torch.bfloat16),
+                         added_cond_kwargs={"image_embeds": img.to(DEV, torch.bfloat16)}).sample.float().cpu()
+        launches = _lib.launch_count() - n0
+        handle.uninstall()
+        if cl:
+            assert launches > 200, launches     # the resnet GroupNorms run in the library too
+    cos = {k: F.cosine_similarity(v.flatten(), ref.flatten(), dim=0).item() for k, v in outs.items()}
+    assert cos[True] >= 0.999 and cos[False] >= 0.999, cos
+    assert cos[True] >= cos[False] - 3e-4, cos
