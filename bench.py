@@ -418,9 +418,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="developer runs under a profiler: skip the host-buffer leg")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay a captured CUDA graph of the denoise step (i2v_adapter_unofficial_b200.graph) in both "
-                         "timed regions; per-kernel rooflines are then timed in an eager pass after them")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
+                    help="(default) replay a captured CUDA graph of the denoise step (i2v_adapter_unofficial_b200.graph) "
+                         "in both timed regions; per-kernel rooflines are then timed in an eager pass after them")
+    ap.add_argument("--eager", dest="graph", action="store_false",
+                    help="launch the step kernel by kernel from Python instead of replaying the captured graph")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -10,6 +10,7 @@
 #include "../../include/i2v_attn_b200.h"
 #include "dense_attn_sm100.cuh"
 #include "dense_attn_pipe_sm100.cuh"
+#include "ip_xattn_stream.cuh"
 #include "generic_attn.cuh"
 #include "norm_layout.cuh"
 #include "temporal_attn.cuh"
@@ -172,6 +173,25 @@ int launch_dense_pipe_cfg(const i2v::DenseParams& Pin, cudaStream_t stream) {
   if (rc) return rc;
   const long long grid = items < di->sms ? items : di->sms;   // persistent: one CTA per SM walks the items
   kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+template <int D, int HG, int MT, int NSTG, int MINB>
+int launch_ip_stream(const i2v::IpStreamParams& P, int sms, cudaStream_t stream) {
+  using Cfg = i2v::IpStreamCfg<D, HG, MT, NSTG, MINB>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = i2v::ip_xattn_stream_kernel<D, HG, MT, NSTG, MINB>;
+  if (!attr_set[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev & 63] = true;
+  }
+  const long long units = (long long)P.batch * (P.heads / HG) * ((P.sq + Cfg::ROWS - 1) / Cfg::ROWS);
+  const long long grid = units < (long long)sms * MINB ? units : (long long)sms * MINB;
+  kern<<<(unsigned)grid, i2v::kIpThreads, Cfg::SMEM_BYTES, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
@@ -514,6 +534,36 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
                 "i2v_ip_xattn_fwd: FAST path needs bf16, supported head dim, image tokens stored right after the text "
                 "tokens and n_txt+n_ip <= tile (d=%d n_txt=%d n_ip=%d contiguous=%d)", d, n_txt, n_ip, (int)contiguous_tokens);
   if (mode != I2V_MODE_GENERIC && fast_ok) {
+    // streaming kernel (HBM-bound design) for the SD1.5 shapes: head dims 40 / 80 / 160 with head groups of 320
+    // columns, rows contiguous across heads, <= 96 keys; tuning key 5 = 1 forces the tcgen05 single-tile kernel
+    const int cfgsel = g_tuning[6];   // experiments: 0 = default configuration per head dim
+    const int hg = d == 40 ? (cfgsel == 1 ? 8 : cfgsel == 2 ? 4 : 2) : d == 80 ? (cfgsel == 1 ? 4 : 2) : d == 160 ? 2 : 0;
+    const bool rows_ok = q->stride_h == d && k_txt->stride_h == d && v_txt->stride_h == d && o->stride_h == d &&
+                         q->stride_s % 8 == 0 && k_txt->stride_s % 8 == 0 && v_txt->stride_s % 8 == 0 &&
+                         o->stride_s % 8 == 0 && q->stride_b % 8 == 0 && k_txt->stride_b % 8 == 0 &&
+                         v_txt->stride_b % 8 == 0 && o->stride_b % 8 == 0;
+    if (hg && heads % hg == 0 && n_txt + n_ip <= i2v::kIpKeys && rows_ok && g_tuning[5] != 1) {
+      if ((rc = check_tensor("q", q, 2, true)) || (rc = check_tensor("k", k_txt, 2, true)) ||
+          (rc = check_tensor("v", v_txt, 2, true)) || (rc = check_tensor("o", o, 2, true)))
+        return rc;
+      i2v::IpStreamParams P;
+      P.q = (const __nv_bfloat16*)q->data; P.k = (const __nv_bfloat16*)k_txt->data;
+      P.v = (const __nv_bfloat16*)v_txt->data; P.o = (__nv_bfloat16*)o->data;
+      P.q_sb = q->stride_b; P.q_ss = q->stride_s; P.k_sb = k_txt->stride_b; P.k_ss = k_txt->stride_s;
+      P.v_sb = v_txt->stride_b; P.v_ss = v_txt->stride_s; P.o_sb = o->stride_b; P.o_ss = o->stride_s;
+      P.batch = batch; P.sq = sq; P.heads = heads; P.nk = n_txt + n_ip; P.n_txt = n_txt; P.kv_group = kv_group;
+      P.scale_log2e = scale * 1.4426950408889634f; P.ip_scale = ip_scale;
+      if (d == 40) {
+        if (cfgsel == 1) return launch_ip_stream<40, 8, 2, 3, 1>(P, di->sms, (cudaStream_t)stream);
+        if (cfgsel == 2) return launch_ip_stream<40, 4, 1, 3, 2>(P, di->sms, (cudaStream_t)stream);
+        return launch_ip_stream<40, 2, 1, 3, 3>(P, di->sms, (cudaStream_t)stream);   // 3 CTAs per SM: 180 us at C2 level 0
+      }
+      if (d == 80) {
+        if (cfgsel == 1) return launch_ip_stream<80, 4, 1, 3, 1>(P, di->sms, (cudaStream_t)stream);
+        return launch_ip_stream<80, 2, 1, 2, 2>(P, di->sms, (cudaStream_t)stream);
+      }
+      return launch_ip_stream<160, 2, 1, 2, 1>(P, di->sms, (cudaStream_t)stream);
+    }
     DenseSeg seg{q, k_txt, v_txt, o, kv_group};
     return launch_dense(&seg, 1, batch, heads, sq, n_txt + n_ip, d, scale, n_txt, ip_scale, (cudaStream_t)stream);
   }

@@ -168,7 +168,8 @@ int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, i
 
 /* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
  * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),
- * key 3: dense-attention tile variant + 1 for head dims <= 48 (see capi.cu). */
+ * key 3: dense-attention tile variant + 1 for head dims <= 48 (see capi.cu), key 5: 1 = IP-Adapter attention on the
+ * tcgen05 single-tile kernel instead of the streaming kernel, key 6: streaming-kernel configuration. */
 int i2v_set_tuning(int key, int value);
 
 #ifdef __cplusplus

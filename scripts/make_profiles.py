@@ -69,7 +69,7 @@ def main():
     with open(os.path.join(OUT, f"{TAG}_launches_step.md"), "w") as f:
         f.write(f"# Launch list of one denoise step ({TAG})\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python bench.py --steps 1 "
-                "--warmup 3 --no-cpu-baseline --no-e2e --profiler-range` (one timed step between cudaProfilerStart/Stop).\n"
+                "--warmup 3 --no-cpu-baseline --no-e2e --eager --profiler-range` (one timed step between cudaProfilerStart/Stop).\n"
                 "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n"
                 f"Total {T:.2f} ms over {sum(cnt.values())} launches; library kernels (`i2v::*`) {ours:.2f} ms = "
                 f"{ours / T * 100:.1f} % in {sum(c for k, c in cnt.items() if 'i2v::' in k)} launches.\n\n"
