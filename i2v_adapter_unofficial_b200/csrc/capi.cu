@@ -733,9 +733,8 @@ int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream) {
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
-  const long long total = rows * (D / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > (long long)di->sms * 32) blocks = (long long)di->sms * 32;
+  long long blocks = (rows + 7) / 8;   // one warp per row, eight warps per CTA
+  if (blocks > (long long)di->sms * 8) blocks = (long long)di->sms * 8;
   i2v::geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, rows, D / 8);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -840,7 +839,7 @@ int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, vo
   i2v::gn_stats_nhwc_kernel<<<grid, block, 2 * C * sizeof(float), (cudaStream_t)stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   const int vg = (N / fg) * G;
-  i2v::gn_finalize_kernel<<<(vg + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
+  i2v::gn_finalize_kernel<<<(vg + 7) / 8, 256, 0, (cudaStream_t)stream>>>(P);   // one warp per (video, group)
   CUDA_TRY(cudaGetLastError());
   i2v::gn_apply_rows_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(P);
   CUDA_TRY(cudaGetLastError());

@@ -106,25 +106,57 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // GEGLU: y[r, c] = x[r, c] * gelu(x[r, D + c]), exact (erf) GELU.  x is [rows, 2D], y is [rows, D].
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result): one reciprocal,
+// one exp2 and a degree-5 Horner chain instead of erff's branchy ~40-instruction expansion -- the GEGLU kernel was
+// ALU-bound on erff (61 % of the HBM roofline), not bandwidth-bound.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = __expf(-ax * ax);
+  return copysignf(fmaf(-p, e, 1.f), x);
+}
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erf_as(g * 0.70710678118654752f)); }
 
+__device__ __forceinline__ uint4 geglu_vec(const uint4 h, const uint4 g) {
+  const uint32_t hin[4] = {h.x, h.y, h.z, h.w}, gin[4] = {g.x, g.y, g.z, g.w};
+  uint32_t out[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // the reference rounds gelu(gate) to bf16 before the product (two PyTorch ops): do the same
+    const uint32_t ge = bf16_pack(gelu_erf(bf16_lo(gin[k])), gelu_erf(bf16_hi(gin[k])));
+    out[k] = bf16_pack(bf16_lo(hin[k]) * bf16_lo(ge), bf16_hi(hin[k]) * bf16_hi(ge));
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// One warp walks a row; every lane keeps up to four 16-byte (h, gate) vector pairs in flight (eight loads before the
+// first use), which is what the HBM latency needs at this occupancy.
 __global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long rows,
                                                     int dvec /* D / 8 */) {
-  const long long total = rows * dvec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / dvec;
-    const int c = (int)(i - r * dvec);
-    const uint4 h = x[r * 2 * dvec + c];
-    const uint4 g = x[r * 2 * dvec + dvec + c];
-    const uint32_t hin[4] = {h.x, h.y, h.z, h.w}, gin[4] = {g.x, g.y, g.z, g.w};
-    uint32_t out[4];
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const uint4* xr = x + r * 2 * dvec;
+    uint4* yr = y + r * dvec;
+    for (int c0 = lane; c0 < dvec; c0 += 128) {
+      uint4 h[4], g[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // the reference rounds gelu(gate) to bf16 before the product (two PyTorch ops): do the same
-      const uint32_t ge = bf16_pack(gelu_erf(bf16_lo(gin[k])), gelu_erf(bf16_hi(gin[k])));
-      out[k] = bf16_pack(bf16_lo(hin[k]) * bf16_lo(ge), bf16_hi(hin[k]) * bf16_hi(ge));
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < dvec) { h[k] = xr[c]; g[k] = xr[dvec + c]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < dvec) yr[c] = geglu_vec(h[k], g[k]);
+      }
     }
-    y[r * dvec + c] = make_uint4(out[0], out[1], out[2], out[3]);
   }
 }
 
@@ -351,21 +383,29 @@ __global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const GnNhwcParams P
   }
 }
 
-__global__ void gn_finalize_kernel(const GnNhwcParams P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (v, g)
+// one warp per (video, group): lanes stride over the fg * CH partials (fixed assignment and a fixed shuffle tree, so
+// the result does not depend on scheduling), then reduce
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnNhwcParams P) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (v, g)
+  const int lane = threadIdx.x & 31;
   const int V = P.N / P.fg;
   if (i >= V * P.G) return;
   const int v = i / P.G, g = i - v * P.G;
   float a = 0.f, b = 0.f;
-  for (int f = 0; f < P.fg; ++f)
-    for (int ch = 0; ch < P.CH; ++ch) {
-      const float* pp = P.partial + ((((long long)v * P.fg + f) * P.CH + ch) * P.G + g) * 2;
-      a += pp[0]; b += pp[1];
-    }
-  const float cnt = (float)P.fg * (float)(P.C / P.G) * (float)P.S;
-  const float mean = a / cnt;
-  P.stats[2 * i] = mean;
-  P.stats[2 * i + 1] = rsqrtf(fmaxf(b / cnt - mean * mean, 0.f) + P.eps);
+  const int n_part = P.fg * P.CH;
+  for (int j = lane; j < n_part; j += 32) {
+    const int f = j / P.CH, ch = j - f * P.CH;
+    const float* pp = P.partial + ((((long long)v * P.fg + f) * P.CH + ch) * P.G + g) * 2;
+    a += pp[0]; b += pp[1];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    const float cnt = (float)P.fg * (float)(P.C / P.G) * (float)P.S;
+    const float mean = a / cnt;
+    P.stats[2 * i] = mean;
+    P.stats[2 * i + 1] = rsqrtf(fmaxf(b / cnt - mean * mean, 0.f) + P.eps);
+  }
 }
 
 __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const GnNhwcParams P) {
