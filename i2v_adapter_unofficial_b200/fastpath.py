@@ -279,7 +279,11 @@ def _make_resnet_forward(module: nn.Module, original: Callable):
         h = module.conv2(h)
         if getattr(module, "conv_shortcut", None) is not None:
             x = module.conv_shortcut(x)
-        out = x + h
+        if ops.is_channels_last(x) and ops.is_channels_last(h):
+            # add on the dense NHWC views: ATen then takes its vectorised kernel (the strided 4-D form ran at 2.7 TB/s)
+            out = (x.permute(0, 2, 3, 1) + h.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        else:
+            out = x + h
         osf = getattr(module, "output_scale_factor", 1.0)
         return out if osf == 1.0 else out / osf
 
