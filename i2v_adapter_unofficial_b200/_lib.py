@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "i2v_reshard_unpack",
     "i2v_set_tuning",
     "i2v_layernorm_fwd",
+    "i2v_layernorm_pre_fwd",
+    "i2v_geglu_ld_fwd",
     "i2v_geglu_fwd",
     "i2v_gn_stats",
     "i2v_gn_apply_transpose",
@@ -39,6 +41,7 @@ EXPORTED_SYMBOLS = (
     "i2v_gn_nhwc_scratch_floats",
     "i2v_gn_nhwc",
     "i2v_rows_residual",
+    "i2v_rows_residual_bias",
 )
 
 
@@ -97,6 +100,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_layernorm_fwd.argtypes = [p, p, p, p, p, ll, i, i, f, p]
     lib.i2v_geglu_fwd.restype = i
     lib.i2v_geglu_fwd.argtypes = [p, p, ll, i, p]
+    lib.i2v_layernorm_pre_fwd.restype = i
+    lib.i2v_layernorm_pre_fwd.argtypes = [p, p, p, p, p, p, ll, i, i, f, p]
+    lib.i2v_geglu_ld_fwd.restype = i
+    lib.i2v_geglu_ld_fwd.argtypes = [p, p, ll, i, i, p]
     lib.i2v_gn_stats.restype = i
     lib.i2v_gn_stats.argtypes = [p, p, i, i, i, i, p]
     lib.i2v_gn_apply_transpose.restype = i
@@ -109,6 +116,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_gn_nhwc.argtypes = [p, p, p, p, p, p, i, i, i, i, i, f, i, i, p]
     lib.i2v_rows_residual.restype = i
     lib.i2v_rows_residual.argtypes = [p, p, p, i, i, i, i, p]
+    lib.i2v_rows_residual_bias.restype = i
+    lib.i2v_rows_residual_bias.argtypes = [p, p, p, p, i, i, i, i, p]
 
 
 def load() -> ctypes.CDLL:

@@ -698,13 +698,13 @@ int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int 
 // ---------------------------------------------------------------------------------------------------------
 extern "C" {
 
-int i2v_layernorm_fwd(const void* x, const void* w, const void* b, const void* pe, void* y, long long rows, int C,
-                      int pe_rows, float eps, void* stream) {
+int i2v_layernorm_pre_fwd(const void* x, const void* pre, const void* w, const void* b, const void* pe, void* y,
+                          long long rows, int C, int pe_rows, float eps, void* stream) {
   if (rows <= 0 || C <= 0) return fail(I2V_ERR_BAD_SHAPE, "layernorm: sizes must be positive");
   if (C % 8 || C > 2048) return fail(I2V_ERR_UNSUPPORTED, "layernorm: C (%d) must be a multiple of 8 and <= 2048", C);
   if (pe != nullptr && pe_rows <= 0) return fail(I2V_ERR_BAD_SHAPE, "layernorm: pe_rows must be positive with pe");
   if (!x || !w || !b || !y) return fail(I2V_ERR_BAD_SHAPE, "layernorm: null pointer");
-  if (!aligned16(x) || !aligned16(w) || !aligned16(b) || !aligned16(y) || (pe && !aligned16(pe)))
+  if (!aligned16(x) || !aligned16(w) || !aligned16(b) || !aligned16(y) || (pe && !aligned16(pe)) || (pre && !aligned16(pre)))
     return fail(I2V_ERR_MISALIGNED, "layernorm: pointers must be 16-byte aligned");
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
@@ -714,20 +714,26 @@ int i2v_layernorm_fwd(const void* x, const void* w, const void* b, const void* p
   const long long blocks = (rows + 7) / 8;
   if (blocks > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "layernorm: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
-  const uint4 *xv = (const uint4*)x, *wv = (const uint4*)w, *bv = (const uint4*)b, *pv = (const uint4*)pe;
+  const uint4 *xv = (const uint4*)x, *wv = (const uint4*)w, *bv = (const uint4*)b, *pv = (const uint4*)pe, *prv = (const uint4*)pre;
   uint4* yv = (uint4*)y;
-  if (maxv <= 2)      i2v::layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
-  else if (maxv <= 3) i2v::layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
-  else if (maxv <= 5) i2v::layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
-  else                i2v::layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps);
+  if (maxv <= 2)      i2v::layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
+  else if (maxv <= 3) i2v::layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
+  else if (maxv <= 5) i2v::layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
+  else                i2v::layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
 }
 
-int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream) {
+int i2v_layernorm_fwd(const void* x, const void* w, const void* b, const void* pe, void* y, long long rows, int C,
+                      int pe_rows, float eps, void* stream) {
+  return i2v_layernorm_pre_fwd(x, nullptr, w, b, pe, y, rows, C, pe_rows, eps, stream);
+}
+
+int i2v_geglu_ld_fwd(const void* x, void* y, long long rows, int D, int ld_out, void* stream) {
   if (rows <= 0 || D <= 0) return fail(I2V_ERR_BAD_SHAPE, "geglu: sizes must be positive");
   if (D % 8) return fail(I2V_ERR_UNSUPPORTED, "geglu: D (%d) must be a multiple of 8", D);
+  if (ld_out != D && ld_out != D + 8) return fail(I2V_ERR_BAD_SHAPE, "geglu: ld_out (%d) must be D or D + 8 (D=%d)", ld_out, D);
   if (!x || !y) return fail(I2V_ERR_BAD_SHAPE, "geglu: null pointer");
   if (!aligned16(x) || !aligned16(y)) return fail(I2V_ERR_MISALIGNED, "geglu: pointers must be 16-byte aligned");
   DeviceInfo* di = nullptr;
@@ -735,7 +741,7 @@ int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream) {
   if (rc) return rc;
   long long blocks = (rows + 7) / 8;   // one warp per row, eight warps per CTA
   if (blocks > (long long)di->sms * 8) blocks = (long long)di->sms * 8;
-  i2v::geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, rows, D / 8);
+  i2v::geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, rows, D / 8, ld_out / 8);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
@@ -749,6 +755,10 @@ static int check_gn_shape(const char* what, int N, int C, int S, int G, int fg) 
     return fail(I2V_ERR_UNSUPPORTED, "%s: needs C %% 64 == 0, S %% 8 == 0 and an even group width (C=%d S=%d G=%d)", what, C, S, G);
   if (N > 65535 || C / 64 > 65535) return fail(I2V_ERR_UNSUPPORTED, "%s: N or C too large for the launch grid", what);
   return 0;
+}
+
+int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream) {
+  return i2v_geglu_ld_fwd(x, y, rows, D, D, stream);
 }
 
 int i2v_gn_stats(const void* x, float* partial, int N, int C, int S, int G, void* stream) {
@@ -847,17 +857,19 @@ int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, vo
   return 0;
 }
 
-int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, int C, int fg, void* stream) {
+int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, void* out, int N, int S, int C, int fg,
+                           void* stream) {
   if (N <= 0 || S <= 0 || C <= 0 || fg <= 0 || C % 8 || N % fg)
     return fail(I2V_ERR_BAD_SHAPE, "rows_residual: bad shape N=%d S=%d C=%d fg=%d", N, S, C, fg);
   if (!y || !res || !out) return fail(I2V_ERR_BAD_SHAPE, "rows_residual: null pointer");
-  if (!aligned16(y) || !aligned16(res) || !aligned16(out))
+  if (!aligned16(y) || !aligned16(res) || !aligned16(out) || (bias && !aligned16(bias)))
     return fail(I2V_ERR_MISALIGNED, "rows_residual: pointers must be 16-byte aligned");
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
   i2v::RowsResidualParams P;
   P.y = (const __nv_bfloat16*)y; P.res = (const __nv_bfloat16*)res; P.out = (__nv_bfloat16*)out;
+  P.bias = (const __nv_bfloat16*)bias;
   P.N = N; P.S = S; P.C = C; P.fg = fg;
   const long long rows = (long long)N * S;
   long long blocks = (rows + 7) / 8;
@@ -866,6 +878,10 @@ int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, i
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
+}
+
+int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, int C, int fg, void* stream) {
+  return i2v_rows_residual_bias(y, res, nullptr, out, N, S, C, fg, stream);
 }
 
 }  // extern "C"

@@ -31,14 +31,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm over the last axis (+ optional additive row table, the sinusoidal positional embedding):
-//   y[r, :] = (x[r, :] - mean) * rstd * w + b  (+ pe[r % pe_rows, :])
-// One warp per row, the row cached in registers (two-pass variance), MAXV 16-byte vectors per lane.
+//   y[r, :] = (x[r, :] - mean) * rstd * w + b  (+ pe[r % pe_rows, :]),   x := x + pre (per channel) when pre != null
+// (the sum is rounded to bf16 first, as the reference's separate add would).  One warp per row, the row cached in registers (two-pass variance), MAXV 16-byte vectors per lane.
 // ---------------------------------------------------------------------------------------------------------------
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                         const uint4* __restrict__ w, const uint4* __restrict__ b,
                                                         const uint4* __restrict__ pe, int pe_rows, long long rows,
-                                                        int nvec /* C / 8 */, float eps) {
+                                                        int nvec /* C / 8 */, float eps,
+                                                        const uint4* __restrict__ pre = nullptr) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -50,6 +51,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict_
     const int c = lane + 32 * i;
     if (c < nvec) {
       v[i] = xr[c];
+      if (pre) {   // x + pre[c]: a per-channel term the producer left out (deferred output-projection biases)
+        const uint4 pv = pre[c];
+        v[i].x = bf16_pack(bf16_lo(v[i].x) + bf16_lo(pv.x), bf16_hi(v[i].x) + bf16_hi(pv.x));
+        v[i].y = bf16_pack(bf16_lo(v[i].y) + bf16_lo(pv.y), bf16_hi(v[i].y) + bf16_hi(pv.y));
+        v[i].z = bf16_pack(bf16_lo(v[i].z) + bf16_lo(pv.z), bf16_hi(v[i].z) + bf16_hi(pv.z));
+        v[i].w = bf16_pack(bf16_lo(v[i].w) + bf16_lo(pv.w), bf16_hi(v[i].w) + bf16_hi(pv.w));
+      }
       s += bf16_lo(v[i].x) + bf16_hi(v[i].x) + bf16_lo(v[i].y) + bf16_hi(v[i].y) + bf16_lo(v[i].z) + bf16_hi(v[i].z) +
            bf16_lo(v[i].w) + bf16_hi(v[i].w);
     }
@@ -136,14 +144,17 @@ __device__ __forceinline__ uint4 geglu_vec(const uint4 h, const uint4 g) {
 
 // One warp walks a row; every lane keeps up to four 16-byte (h, gate) vector pairs in flight (eight loads before the
 // first use), which is what the HBM latency needs at this occupancy.
+// ld_out_vec >= dvec: output row pitch in vectors; with ld_out_vec == dvec + 1 the extra vector of every row is set to
+// (1, 0, ..., 0) -- a ones column that lets the following GEMM carry its bias as one more weight column.
 __global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long rows,
-                                                    int dvec /* D / 8 */) {
+                                                    int dvec /* D / 8 */, int ld_out_vec) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp0; r < rows; r += nwarps) {
     const uint4* xr = x + r * 2 * dvec;
-    uint4* yr = y + r * dvec;
+    uint4* yr = y + r * ld_out_vec;
+    if (ld_out_vec > dvec && lane == 0) yr[dvec] = make_uint4(0x00003F80u, 0u, 0u, 0u);   // bf16 1.0 then zeros
     for (int c0 = lane; c0 < dvec; c0 += 128) {
       uint4 h[4], g[4];
 #pragma unroll
@@ -456,6 +467,7 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const GnNhwcParams P
 struct RowsResidualParams {
   const __nv_bfloat16* y;
   const __nv_bfloat16* res;
+  const __nv_bfloat16* bias;   // [C] or null: added per channel (a convolution / projection bias folded into this pass)
   __nv_bfloat16* out;
   int N, S, C, fg;
 };
@@ -473,9 +485,21 @@ __global__ void __launch_bounds__(256) rows_residual_kernel(const RowsResidualPa
     for (int cv = lane; cv < VC; cv += 32) {
       const uint4 a = ysrc[cv], b = rsrc[cv];
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+      uint32_t cw[4] = {0u, 0u, 0u, 0u};
+      if (P.bias) {
+        const uint4 c = reinterpret_cast<const uint4*>(P.bias)[cv];
+        cw[0] = c.x; cw[1] = c.y; cw[2] = c.z; cw[3] = c.w;
+      }
       uint32_t o[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = bf16_pack(bf16_lo(aw[k]) + bf16_lo(bw[k]), bf16_hi(aw[k]) + bf16_hi(bw[k]));
+      for (int k = 0; k < 4; ++k) {
+        float lo = bf16_lo(aw[k]), hi = bf16_hi(aw[k]);
+        if (P.bias) {   // the reference rounds y + bias first (the producer's own op), then adds the residual
+          const uint32_t r = bf16_pack(lo + bf16_lo(cw[k]), hi + bf16_hi(cw[k]));
+          lo = bf16_lo(r); hi = bf16_hi(r);
+        }
+        o[k] = bf16_pack(lo + bf16_lo(bw[k]), hi + bf16_hi(bw[k]));
+      }
       dst[cv] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }

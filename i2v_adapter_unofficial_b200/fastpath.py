@@ -41,11 +41,14 @@ def _fast_ok(x: torch.Tensor, module: nn.Module) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and not module.training and not torch.is_grad_enabled()
 
 
-def _ln(x: torch.Tensor, norm: nn.LayerNorm, pe: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _ln(x: torch.Tensor, norm: nn.LayerNorm, pe: Optional[torch.Tensor] = None,
+        pre: Optional[torch.Tensor] = None) -> torch.Tensor:
     if norm.weight is None or norm.bias is None:
+        if pre is not None:
+            x = x + pre
         y = F.layer_norm(x, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
         return y if pe is None else y + pe
-    return ops.layernorm(x.contiguous(), norm.weight, norm.bias, norm.eps, pe)
+    return ops.layernorm(x.contiguous(), norm.weight, norm.bias, norm.eps, pe, pre)
 
 
 def _ff(ff: nn.Module, x: torch.Tensor) -> torch.Tensor:
@@ -54,6 +57,45 @@ def _ff(ff: nn.Module, x: torch.Tensor) -> torch.Tensor:
     h = ops.geglu(F.linear(x, proj.weight, proj.bias))
     out = ff.net[2]
     return F.linear(h, out.weight, out.bias)
+
+
+class _Deferred:
+    """Per-block cache of the deferred-bias vectors and of the feed-forward's augmented output weight.
+
+    With the residual add of every sub-layer riding in its output GEMM (``processors._out_proj``), the output biases
+    b1 (attn1 [+ i2v_adapter]), b2 (attn2), b3 (ff) are constants that still have to reach the residual stream:
+    LayerNorm 2 reads ``hidden + b1``, LayerNorm 3 reads ``hidden + b1 + b2`` (``pre`` of the LayerNorm kernel) and the
+    last GEMM of the block gets ``[W_ff2 | b1 + b2 + b3 | 0]`` against a GEGLU output with a ones column, so the block
+    returns the exact residual stream with no separate add or bias pass."""
+
+    def __init__(self):
+        self.key = None
+        self.val = None
+
+    @staticmethod
+    def _sig(t):
+        return None if t is None else (t.data_ptr(), t._version)
+
+    def get1(self, b1, like: torch.Tensor):
+        key = (self._sig(b1), like.dtype, like.device)
+        if key != getattr(self, "key1", None):
+            self.val1 = b1.to(like.dtype).contiguous()
+            self.key1 = key
+        return self.val1
+
+    def get(self, b1, b2, ff_out: nn.Linear, like: torch.Tensor):
+        key = (self._sig(b1), self._sig(b2), self._sig(ff_out.weight), self._sig(ff_out.bias), like.dtype, like.device)
+        if key != self.key:
+            C = ff_out.weight.shape[0]
+            zero = torch.zeros(C, dtype=torch.float32, device=like.device)
+            p1 = zero if b1 is None else b1.float()
+            p2 = p1 + (zero if b2 is None else b2.float())
+            p3 = p2 + (zero if ff_out.bias is None else ff_out.bias.float())
+            w_aug = torch.cat([ff_out.weight.float(), p3[:, None], ff_out.weight.new_zeros(C, 7).float()], dim=1)
+            self.val = (p1.to(like.dtype).contiguous(), p2.to(like.dtype).contiguous(),
+                        w_aug.to(like.dtype).contiguous())
+            self.key = key
+        return self.val
 
 
 def _is_geglu_ff(ff: nn.Module) -> bool:
@@ -81,40 +123,79 @@ class _PE:
 # ----------------------------------------------------------------------------------------------------------------
 # transformer blocks
 # ----------------------------------------------------------------------------------------------------------------
-def _block_forward_fast(self, hidden_states, encoder_hidden_states, enable_cross_frame_attn, num_frames, kw, pe_cache):
+def _fused_residual_ok(self) -> bool:
+    """All sub-layers of the block can take their residual inside the output GEMM (our processors, plain GEGLU ff)."""
+    from .processors import B200AttnProcessor, B200IPAdapterAttnProcessor, B200TemporalAttnProcessor
+
+    def ours(attn):
+        proc = attn.get_processor() if hasattr(attn, "get_processor") else None
+        return isinstance(proc, (B200AttnProcessor, B200IPAdapterAttnProcessor, B200TemporalAttnProcessor))
+
+    return (self.attn2 is not None and ours(self.attn1) and ours(self.attn2)
+            and self.ff.net[2].weight.shape[1] % 8 == 0 and not self.only_cross_attention)
+
+
+def _block_forward_fast(self, hidden_states, encoder_hidden_states, enable_cross_frame_attn, num_frames, kw, pe_cache,
+                        deferred=None):
     """Shared body of I2VAdapterTransformerBlock.forward (src/modules/i2v_adapter.py:420-565) and the diffusers
-    BasicTransformerBlock.forward it extends (layer_norm flavour)."""
+    BasicTransformerBlock.forward it extends (layer_norm flavour).
+
+    With ``deferred`` (a ``_Deferred`` cache; our processors installed) the three residual adds (:501, :533, :561)
+    ride in the output GEMMs of attn1 / attn2 / ff and their biases are deferred as described in ``_Deferred``."""
+    from .processors import RESIDUAL_KW
+
     pe = None
     if self.pos_embed is not None:
         pe = pe_cache.get(self.pos_embed, hidden_states.shape[1], hidden_states)
+    fuse = deferred is not None and hidden_states.is_contiguous()
     norm_h = _ln(hidden_states, self.norm1, pe)                                                   # :445, :458-459
+    kw1 = dict(kw, **{RESIDUAL_KW: hidden_states}) if fuse else kw
     attn_output = self.attn1(norm_h, encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
-                             attention_mask=None, **kw)                                           # :468-473
+                             attention_mask=None, **kw1)                                          # :468-473
+    proc1 = self.attn1.get_processor() if hasattr(self.attn1, "get_processor") else None
+    fused1 = fuse and getattr(proc1, "fused_residual", False)
+    b1 = getattr(proc1, "deferred_bias", None) if fused1 else None
     if enable_cross_frame_attn:
         batch_size = hidden_states.shape[0]
         if num_frames is None:
             raise ValueError("`num_frames` must be provided when `enable_cross_frame_attn` is True.")
         if batch_size % num_frames != 0:
             raise ValueError(f"Batch size {batch_size} must be divisible by the number of frames {num_frames}.")
-        proc = self.attn1.get_processor() if hasattr(self.attn1, "get_processor") else None
-        state = getattr(proc, "state", None)
+        state = getattr(proc1, "state", None)
         if state is not None and state.cross_done:
             state.cross_done = False          # attn1's processor already returned self + cross-frame (one launch)
         else:
             first = norm_h[0:batch_size:num_frames].repeat_interleave(num_frames, dim=0)          # :484-485
             attn_output = attn_output + self.i2v_adapter(norm_h, encoder_hidden_states=first, attention_mask=None,
                                                          **kw)                                    # :487-494
-    hidden_states = attn_output + hidden_states                                                   # :501
+    hidden_states = attn_output if fused1 else attn_output + hidden_states                        # :501
+    b2 = None
     if self.attn2 is not None:
-        norm_h = _ln(hidden_states, self.norm2, pe)                                               # :514, :524-525
-        attn_output = self.attn2(norm_h, encoder_hidden_states=encoder_hidden_states, attention_mask=None, **kw)
-        hidden_states = attn_output + hidden_states                                               # :533
+        pre1 = None
+        if fused1 and b1 is not None:
+            pre1 = deferred.get1(b1, hidden_states)
+        norm_h = _ln(hidden_states, self.norm2, pe, pre1)                                         # :514, :524-525
+        kw2 = dict(kw, **{RESIDUAL_KW: hidden_states}) if fuse else kw
+        attn_output = self.attn2(norm_h, encoder_hidden_states=encoder_hidden_states, attention_mask=None, **kw2)
+        proc2 = self.attn2.get_processor() if hasattr(self.attn2, "get_processor") else None
+        fused2 = fuse and getattr(proc2, "fused_residual", False)
+        b2 = getattr(proc2, "deferred_bias", None) if fused2 else None
+        hidden_states = attn_output if fused2 else attn_output + hidden_states                    # :533
+    if fuse:
+        p1, p2, w_aug = deferred.get(b1, b2, self.ff.net[2], hidden_states)
+        pending = b1 is not None or b2 is not None
+        norm_h = _ln(hidden_states, self.norm3, None, p2 if pending else None)                    # :539
+        proj = self.ff.net[0].proj
+        h = ops.geglu(F.linear(norm_h, proj.weight, proj.bias), ones_column=True)                 # [.., 4C + 8]
+        C = hidden_states.shape[-1]
+        return torch.addmm(hidden_states.view(-1, C), h.view(-1, h.shape[-1]), w_aug.t()).view(hidden_states.shape)
     hidden_states = _ff(self.ff, _ln(hidden_states, self.norm3)) + hidden_states                  # :539-561
     return hidden_states
 
 
 def _make_block_forward(module: nn.Module, original: Callable, is_i2v: bool):
     pe_cache = _PE()
+    deferred = _Deferred()
 
     @functools.wraps(original)  # keeps the reference signature visible to inspect.signature (install()'s hooks bind it)
     def forward(hidden_states, *args, **kwargs):
@@ -136,7 +217,8 @@ def _make_block_forward(module: nn.Module, original: Callable, is_i2v: bool):
         kw.pop("gligen", None)
         return _block_forward_fast(module, hidden_states, bound.get("encoder_hidden_states"),
                                    bool(bound.get("enable_cross_frame_attn", False)) if is_i2v else False,
-                                   bound.get("num_frames") if is_i2v else None, kw, pe_cache)
+                                   bound.get("num_frames") if is_i2v else None, kw, pe_cache,
+                                   deferred if _fused_residual_ok(module) else None)
 
     return forward
 
@@ -266,24 +348,31 @@ def _make_resnet_forward(module: nn.Module, original: Callable):
                   and not getattr(module, "up", False) and not getattr(module, "down", False)
                   and getattr(module, "upsample", None) is None and getattr(module, "downsample", None) is None
                   and getattr(module.dropout, "p", 0.0) == 0.0 and module.conv1.out_channels % 8 == 0
+                  and isinstance(module.conv1, nn.Conv2d) and isinstance(module.conv2, nn.Conv2d)
+                  and module.conv1.padding_mode == "zeros" and module.conv2.padding_mode == "zeros"
                   and module.conv1.out_channels <= 4096)
         if not simple:
             return original(x, temb, *args, **kwargs)
         n1, n2 = module.norm1, module.norm2
+        c1, c2 = module.conv1, module.conv2
         h = ops.group_norm_nhwc(x, n1.weight, n1.bias, n1.num_groups, n1.eps, 1, silu=True)
-        h = module.conv1(h)
+        # cuDNN applies a convolution bias as a separate broadcast-add pass; both biases of the block are per-channel
+        # constants that the next bandwidth kernel can carry instead: conv1's joins the time-embedding term of norm2,
+        # conv2's the residual add
+        h = F.conv2d(h, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
         t = module.time_emb_proj(F.silu(temb))
+        if c1.bias is not None:
+            t = t + c1.bias
         if not ops.is_channels_last(h):
             h = h.contiguous(memory_format=torch.channels_last)
         h = ops.group_norm_nhwc(h, n2.weight, n2.bias, n2.num_groups, n2.eps, 1, silu=True, add=t)
-        h = module.conv2(h)
+        h = F.conv2d(h, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
         if getattr(module, "conv_shortcut", None) is not None:
             x = module.conv_shortcut(x)
         if ops.is_channels_last(x) and ops.is_channels_last(h):
-            # add on the dense NHWC views: ATen then takes its vectorised kernel (the strided 4-D form ran at 2.7 TB/s)
-            out = (x.permute(0, 2, 3, 1) + h.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+            out = ops.nhwc_add(x, h, c2.bias)          # x + h + bias[c] in one pass
         else:
-            out = x + h
+            out = x + (h if c2.bias is None else h + c2.bias[None, :, None, None])
         osf = getattr(module, "output_scale_factor", 1.0)
         return out if osf == 1.0 else out / osf
 

@@ -236,31 +236,36 @@ def _require_bf16_contig(*tensors: torch.Tensor) -> torch.device:
 
 
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
-              pe: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """LayerNorm over the last axis; ``pe`` [F, C] is added per row with ``row % F`` (rows of a [N, F, C] tensor)."""
-    dev = _require_bf16_contig(x, weight, bias) if pe is None else _require_bf16_contig(x, weight, bias, pe)
+              pe: Optional[torch.Tensor] = None, pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm over the last axis; ``pe`` [F, C] is added per row with ``row % F`` (rows of a [N, F, C] tensor);
+    ``pre`` [C] is added to x before the statistics (a deferred per-channel bias of the producer)."""
+    dev = _require_bf16_contig(*[t for t in (x, weight, bias, pe, pre) if t is not None])
     C = x.shape[-1]
     rows = x.numel() // C
     if pe is not None and (pe.dim() != 2 or pe.shape[1] != C or x.dim() < 2 or x.shape[-2] != pe.shape[0]):
         raise ValueError(f"pe {tuple(pe.shape)} does not match x {tuple(x.shape)}: need pe [x.shape[-2], C]")
+    if pre is not None and tuple(pre.shape) != (C,):
+        raise ValueError(f"pre {tuple(pre.shape)} must be [{C}]")
     y = torch.empty_like(x)
     lib = _lib.load()
     with _on_device(dev):
-        _lib.check(lib.i2v_layernorm_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(),
-                                         None if pe is None else pe.data_ptr(), y.data_ptr(), rows, C,
-                                         0 if pe is None else pe.shape[0], float(eps), _stream(dev)))
+        _lib.check(lib.i2v_layernorm_pre_fwd(x.data_ptr(), None if pre is None else pre.data_ptr(), weight.data_ptr(),
+                                             bias.data_ptr(), None if pe is None else pe.data_ptr(), y.data_ptr(), rows,
+                                             C, 0 if pe is None else pe.shape[0], float(eps), _stream(dev)))
     return y
 
 
-def geglu(x: torch.Tensor) -> torch.Tensor:
-    """x [..., 2*D] -> x[..., :D] * gelu(x[..., D:])."""
+def geglu(x: torch.Tensor, ones_column: bool = False) -> torch.Tensor:
+    """x [..., 2*D] -> x[..., :D] * gelu(x[..., D:]).  With ``ones_column`` the result is [..., D + 8] whose extra
+    columns are (1, 0, ..., 0): the following GEMM then carries its bias as weight column D."""
     dev = _require_bf16_contig(x)
     D = x.shape[-1] // 2
     rows = x.numel() // (2 * D)
-    y = torch.empty(x.shape[:-1] + (D,), dtype=x.dtype, device=dev)
+    ld = D + 8 if ones_column else D
+    y = torch.empty(x.shape[:-1] + (ld,), dtype=x.dtype, device=dev)
     lib = _lib.load()
     with _on_device(dev):
-        _lib.check(lib.i2v_geglu_fwd(x.data_ptr(), y.data_ptr(), rows, D, _stream(dev)))
+        _lib.check(lib.i2v_geglu_ld_fwd(x.data_ptr(), y.data_ptr(), rows, D, ld, _stream(dev)))
     return y
 
 
@@ -341,6 +346,23 @@ def positions_to_nhwc_residual(y: torch.Tensor, residual: torch.Tensor, frames_p
     with _on_device(y.device):
         _lib.check(lib.i2v_rows_residual(y.data_ptr(), residual.data_ptr(), out.data_ptr(), N, h * w, C, frames_per_stat,
                                          _stream(y.device)))
+    return out
+
+
+def nhwc_add(x: torch.Tensor, y: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x + (y + bias[c]) for two channels-last (N, C, h, w) tensors, one pass (ResnetBlock2D's residual add with the
+    second convolution's bias folded in)."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and is_channels_last(x) and is_channels_last(y)
+            and x.shape == y.shape and y.dtype == x.dtype):
+        raise RuntimeError("nhwc_add: needs two CUDA bf16 channels-last tensors of one shape (no CPU fallback)")
+    N, C, h, w = x.shape
+    out = torch.empty_like(x)
+    if bias is not None:
+        bias = bias.to(dtype=x.dtype).contiguous()
+    lib = _lib.load()
+    with _on_device(x.device):
+        _lib.check(lib.i2v_rows_residual_bias(y.data_ptr(), x.data_ptr(), None if bias is None else bias.data_ptr(),
+                                              out.data_ptr(), N, h * w, C, 1, _stream(x.device)))
     return out
 
 

@@ -123,6 +123,32 @@ def _check_supported(attn, attention_mask, what: str) -> None:
             raise NotImplementedError(f"{what}: Attention.{name} is not used on the SD1.5 path and is not supported")
 
 
+RESIDUAL_KW = "_b200_residual"   # kwarg the module-level fast path uses to hand a processor the block's residual stream
+
+
+def _out_proj(proc, attn, o: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], kwargs) -> torch.Tensor:
+    """``to_out`` of an Attention (Linear + Dropout(0)) on o [B, S, K].
+
+    When the caller passes the residual stream (``fastpath._block_forward_fast``), the residual add rides in the GEMM
+    as its beta = 1 term (``torch.addmm``: one cuBLAS launch, no separate add pass) and the bias is *not* applied:
+    it is left in ``proc.deferred_bias`` for the caller, which folds the deferred biases of a block into the next
+    LayerNorm read and into the feed-forward's last GEMM.  ``proc.fused_residual`` tells the
+    caller which of the two results it got."""
+    res = kwargs.get(RESIDUAL_KW)
+    drop = attn.to_out[1] if len(attn.to_out) > 1 else None
+    if (res is not None and o.dim() == 3 and res.shape[:-1] == o.shape[:-1] and res.shape[-1] == weight.shape[0]
+            and res.dtype == o.dtype and not getattr(attn, "residual_connection", False)
+            and getattr(attn, "rescale_output_factor", 1.0) == 1.0 and getattr(drop, "p", 0.0) == 0.0):
+        out = torch.addmm(res.reshape(-1, res.shape[-1]), o.reshape(-1, o.shape[-1]), weight.t()).view(res.shape)
+        proc.deferred_bias = bias
+        proc.fused_residual = True
+        return out
+    proc.fused_residual = False
+    proc.deferred_bias = None
+    out = F.linear(o, weight, bias)
+    return out if drop is None else drop(out)
+
+
 def _finish(attn, o: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
     if getattr(attn, "residual_connection", False):
         o = o + residual
@@ -149,6 +175,9 @@ class B200AttnProcessor:
 
     ``kv_replicated`` (set by ``install`` for spatial attn2 without IP-Adapter): the context rows of the frames of
     a video are identical when the UNet-level hook says so, so K/V are projected once per video."""
+
+    fused_residual = False   # set per call by _out_proj: the result already contains the caller's residual
+    deferred_bias = None     # ... and this output-projection bias has not been applied
 
     def __init__(self, mode: int = MODE_AUTO, context: Optional[RuntimeContext] = None,
                  state: Optional[BlockState] = None):
@@ -188,6 +217,10 @@ class B200AttnProcessor:
             q = attn.to_q(x).view(B, S, H, d)
             kv = F.linear(ctx, w[0], w[1]).view(ctx.shape[0], ctx.shape[1], 2, H, d)
             o = ops.sdpa(q, kv[:, :, 0], kv[:, :, 1], group, attn.scale, self.mode)
+        if shape4 is None:
+            return _finish(attn, _out_proj(self, attn, o.view(B, S, inner), attn.to_out[0].weight, attn.to_out[0].bias,
+                                           kwargs), residual)
+        self.fused_residual = False
         o = attn.to_out[0](o.view(B, S, inner))
         o = attn.to_out[1](o)
         return _finish(attn, _from_3d(o, shape4), residual)
@@ -260,8 +293,7 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
             kvx = F.linear(first, wxa[0], wxa[1]).view(BF // Fr, S, 2, H, dp)
             o = ops.fused_self_xframe_aug(y[:, :, 0], y[:, :, 1], y[:, :, 2], y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1],
                                           Fr, d)
-            out = F.linear(o.view(BF, S, 2 * inner), w_out[0], w_out[1])
-            out = attn.to_out[1](out)
+            out = _out_proj(self, attn, o.view(BF, S, 2 * inner), w_out[0], w_out[1], kwargs)
             st.cross_done = True
             return out
         y = F.linear(x, w_in[0], w_in[1]).view(BF, S, 4, H, d)
@@ -273,8 +305,7 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
             kvx = F.linear(first, w_x[0], w_x[1]).view(BF // Fr, S, 2, H, d)
         o = ops.fused_self_xframe(y[:, :, 0], y[:, :, 1], y[:, :, 2], y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1], Fr,
                                   attn.scale, self.mode)
-        out = F.linear(o.view(BF, S, 2 * inner), w_out[0], w_out[1])
-        out = attn.to_out[1](out)
+        out = _out_proj(self, attn, o.view(BF, S, 2 * inner), w_out[0], w_out[1], kwargs)
         st.cross_done = True
         return out
 
@@ -380,6 +411,10 @@ class B200IPAdapterAttnProcessor(nn.Module):
         kv2[:, :end] = F.linear(ctx[:, :end], w_txt[0], w_txt[1])
         kv2[:, end:] = F.linear(ctx[:, end:], w_ip)
         o = ops.ip_xattn(q, kv[:, :, 0], kv[:, :, 1], end, self.scale, group, attn.scale, self.mode)
+        if shape4 is None:
+            return _finish(attn, _out_proj(self, attn, o.view(B, S, inner), attn.to_out[0].weight, attn.to_out[0].bias,
+                                           kwargs), residual)
+        self.fused_residual = False
         o = attn.to_out[0](o.view(B, S, inner))
         o = attn.to_out[1](o)
         return _finish(attn, _from_3d(o, shape4), residual)
@@ -389,6 +424,9 @@ class B200TemporalAttnProcessor:
     """Motion-module temporal self-attention (both attn1 and attn2 of the temporal BasicTransformerBlock are
     self-attentions: ``double_self_attention=True``).  hidden_states is [B*S, F, C]."""
 
+    fused_residual = False   # set per call by _out_proj: the result already contains the caller's residual
+    deferred_bias = None     # ... and this output-projection bias has not been applied
+
     def __init__(self, mode: int = MODE_AUTO):
         self.mode = mode
         self._w_qkv = _PackedWeights()
@@ -397,7 +435,9 @@ class B200TemporalAttnProcessor:
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
                  scale: float = 1.0, **kwargs):
         if encoder_hidden_states is not None or hidden_states.dim() != 3:
-            return self._generic(attn, hidden_states, encoder_hidden_states, attention_mask, temb, scale, **kwargs)
+            out = self._generic(attn, hidden_states, encoder_hidden_states, attention_mask, temb, scale, **kwargs)
+            self.fused_residual, self.deferred_bias = self._generic.fused_residual, self._generic.deferred_bias
+            return out
         _check_supported(attn, attention_mask, type(self).__name__)
         x = hidden_states
         N, Fr, _ = x.shape
@@ -411,9 +451,8 @@ class B200TemporalAttnProcessor:
                                                attn.to_q.weight)))
         qkv = F.linear(x, w[0], w[1]).view(N, Fr, 3, H, d)
         o = ops.temporal_attn(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], attn.scale, self.mode)
-        o = attn.to_out[0](o.view(N, Fr, inner))
-        o = attn.to_out[1](o)
-        return _finish(attn, o, hidden_states)
+        return _finish(attn, _out_proj(self, attn, o.view(N, Fr, inner), attn.to_out[0].weight, attn.to_out[0].bias,
+                                       kwargs), hidden_states)
 
 
 # ----------------------------------------------------------------------------------------------------------

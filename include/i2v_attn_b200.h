@@ -135,8 +135,15 @@ int i2v_reshard_unpack(const void* src, void* dst, int videos, int f_local, int 
  *   that r % pe_rows is the frame index ([B*S, F, C] of the motion module). */
 int i2v_layernorm_fwd(const void* x, const void* w, const void* b, const void* pe, void* y, long long rows, int C,
                       int pe_rows, float eps, void* stream);
+/* i2v_layernorm_pre_fwd: the same with x := x + pre[c] first (pre: [C] or NULL) -- the per-channel constant a producer
+ *   GEMM left out, see fastpath.py: output-projection biases are deferred so the residual add rides in the GEMM. */
+int i2v_layernorm_pre_fwd(const void* x, const void* pre, const void* w, const void* b, const void* pe, void* y,
+                          long long rows, int C, int pe_rows, float eps, void* stream);
 /* i2v_geglu_fwd: y[r, c] = x[r, c] * gelu(x[r, D + c]) (erf GELU).  x: [rows, 2*D], y: [rows, D], D % 8 == 0. */
 int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream);
+/* i2v_geglu_ld_fwd: y has row pitch ld_out = D or D + 8; with D + 8 the extra columns are (1, 0, .., 0): a ones column
+ *   so that the following GEMM can carry its bias as one more weight column (and its residual as the beta = 1 term). */
+int i2v_geglu_ld_fwd(const void* x, void* y, long long rows, int D, int ld_out, void* stream);
 /* GroupNorm + layout change in two passes over x [N, C, S] (NCHW, S = h*w), G groups, statistics shared by `fg`
  * consecutive batch entries (fg = 1: the spatial transformer's per-frame GroupNorm; fg = num_frames: the motion module's
  * GroupNorm over (C/G, F, h, w) per video, N = videos * fg, frame index fastest):
@@ -165,6 +172,10 @@ int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, vo
 /* out[n, s, :] = y[(v*S + s)*fg + f, :] + res[n, s, :] with n = v*fg + f: the motion module's way back to the
  * frame-major channels-last activation, fused with its residual add. */
 int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, int C, int fg, void* stream);
+/* ... + bias[c] (NULL allowed): out = (y + bias) + res.  With fg = 1 this is ResnetBlock2D's `input + conv2(...)` with
+ * conv2's bias folded in (cuDNN would spend a separate broadcast-add pass on it). */
+int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, void* out, int N, int S, int C, int fg,
+                           void* stream);
 
 /* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
  * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),
