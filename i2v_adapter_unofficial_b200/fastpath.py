@@ -135,21 +135,25 @@ def _fused_residual_ok(self) -> bool:
             and self.ff.net[2].weight.shape[1] % 8 == 0 and not self.only_cross_attention)
 
 
+OWNED_INPUT_FLAG = "_b200_owned_input"   # set by our wrapper forwards right before calling a block: the tokens tensor
+#                                          is theirs alone, the block may accumulate its first residual into it in place
+
+
 def _block_forward_fast(self, hidden_states, encoder_hidden_states, enable_cross_frame_attn, num_frames, kw, pe_cache,
-                        deferred=None):
+                        deferred=None, owned_input=False):
     """Shared body of I2VAdapterTransformerBlock.forward (src/modules/i2v_adapter.py:420-565) and the diffusers
     BasicTransformerBlock.forward it extends (layer_norm flavour).
 
     With ``deferred`` (a ``_Deferred`` cache; our processors installed) the three residual adds (:501, :533, :561)
     ride in the output GEMMs of attn1 / attn2 / ff and their biases are deferred as described in ``_Deferred``."""
-    from .processors import RESIDUAL_KW
+    from .processors import RESIDUAL_INPLACE_KW, RESIDUAL_KW
 
     pe = None
     if self.pos_embed is not None:
         pe = pe_cache.get(self.pos_embed, hidden_states.shape[1], hidden_states)
     fuse = deferred is not None and hidden_states.is_contiguous()
     norm_h = _ln(hidden_states, self.norm1, pe)                                                   # :445, :458-459
-    kw1 = dict(kw, **{RESIDUAL_KW: hidden_states}) if fuse else kw
+    kw1 = dict(kw, **{RESIDUAL_KW: hidden_states, RESIDUAL_INPLACE_KW: bool(owned_input)}) if fuse else kw
     attn_output = self.attn1(norm_h, encoder_hidden_states=encoder_hidden_states if self.only_cross_attention else None,
                              attention_mask=None, **kw1)                                          # :468-473
     proc1 = self.attn1.get_processor() if hasattr(self.attn1, "get_processor") else None
@@ -175,7 +179,8 @@ def _block_forward_fast(self, hidden_states, encoder_hidden_states, enable_cross
         if fused1 and b1 is not None:
             pre1 = deferred.get1(b1, hidden_states)
         norm_h = _ln(hidden_states, self.norm2, pe, pre1)                                         # :514, :524-525
-        kw2 = dict(kw, **{RESIDUAL_KW: hidden_states}) if fuse else kw
+        # hidden_states is an intermediate of this block from here on: the GEMM may accumulate into it in place
+        kw2 = dict(kw, **{RESIDUAL_KW: hidden_states, RESIDUAL_INPLACE_KW: True}) if fuse else kw
         attn_output = self.attn2(norm_h, encoder_hidden_states=encoder_hidden_states, attention_mask=None, **kw2)
         proc2 = self.attn2.get_processor() if hasattr(self.attn2, "get_processor") else None
         fused2 = fuse and getattr(proc2, "fused_residual", False)
@@ -188,6 +193,9 @@ def _block_forward_fast(self, hidden_states, encoder_hidden_states, enable_cross
         proj = self.ff.net[0].proj
         h = ops.geglu(F.linear(norm_h, proj.weight, proj.bias), ones_column=True)                 # [.., 4C + 8]
         C = hidden_states.shape[-1]
+        if self.attn2 is not None:   # hidden_states is this block's own tensor (see above): accumulate in place
+            hidden_states.view(-1, C).addmm_(h.view(-1, h.shape[-1]), w_aug.t())
+            return hidden_states
         return torch.addmm(hidden_states.view(-1, C), h.view(-1, h.shape[-1]), w_aug.t()).view(hidden_states.shape)
     hidden_states = _ff(self.ff, _ln(hidden_states, self.norm3)) + hidden_states                  # :539-561
     return hidden_states
@@ -206,6 +214,7 @@ def _make_block_forward(module: nn.Module, original: Callable, is_i2v: bool):
                   "cross_attention_kwargs", "class_labels"))
         bound: Dict[str, Any] = dict(zip(names, args))
         bound.update(kwargs)
+        owned = module.__dict__.pop(OWNED_INPUT_FLAG, False)
         simple = (_fast_ok(hidden_states, module) and hidden_states.dim() == 3 and hidden_states.shape[-1] % 8 == 0
                   and bound.get("attention_mask") is None and bound.get("encoder_attention_mask") is None
                   and len(args) <= len(names) and set(kwargs) <= set(names)
@@ -218,7 +227,7 @@ def _make_block_forward(module: nn.Module, original: Callable, is_i2v: bool):
         return _block_forward_fast(module, hidden_states, bound.get("encoder_hidden_states"),
                                    bool(bound.get("enable_cross_frame_attn", False)) if is_i2v else False,
                                    bound.get("num_frames") if is_i2v else None, kw, pe_cache,
-                                   deferred if _fused_residual_ok(module) else None)
+                                   deferred if _fused_residual_ok(module) else None, owned)
 
     return forward
 
@@ -272,6 +281,7 @@ def _make_transformer2d_forward(module: nn.Module, original: Callable):
         inner = module.proj_in.weight.shape[0]
         tokens = F.linear(tokens, module.proj_in.weight.reshape(inner, C), module.proj_in.bias)
         for block in module.transformer_blocks:                                                  # :244-296
+            block.__dict__[OWNED_INPUT_FLAG] = True   # `tokens` is a fresh GEMM output / the previous block's result
             tokens = block(tokens, enable_cross_frame_attn=bound.get("enable_cross_frame_attn", False),
                            num_frames=bound.get("num_frames"), attention_mask=None,
                            encoder_hidden_states=bound.get("encoder_hidden_states"), encoder_attention_mask=None,
@@ -315,6 +325,7 @@ def _make_temporal_forward(module: nn.Module, original: Callable):
             x = ops.group_norm_tokens(hidden_states, norm.weight, norm.bias, norm.num_groups, norm.eps, num_frames)
         x = module.proj_in(x)
         for block in module.transformer_blocks:
+            block.__dict__[OWNED_INPUT_FLAG] = True
             x = block(x, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
                       cross_attention_kwargs=cross_attention_kwargs, class_labels=class_labels)
         x = module.proj_out(x)

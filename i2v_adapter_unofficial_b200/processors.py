@@ -124,6 +124,7 @@ def _check_supported(attn, attention_mask, what: str) -> None:
 
 
 RESIDUAL_KW = "_b200_residual"   # kwarg the module-level fast path uses to hand a processor the block's residual stream
+RESIDUAL_INPLACE_KW = "_b200_residual_inplace"   # ... and to say that the processor may accumulate into it in place
 
 
 def _out_proj(proc, attn, o: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], kwargs) -> torch.Tensor:
@@ -139,7 +140,12 @@ def _out_proj(proc, attn, o: torch.Tensor, weight: torch.Tensor, bias: Optional[
     if (res is not None and o.dim() == 3 and res.shape[:-1] == o.shape[:-1] and res.shape[-1] == weight.shape[0]
             and res.dtype == o.dtype and not getattr(attn, "residual_connection", False)
             and getattr(attn, "rescale_output_factor", 1.0) == 1.0 and getattr(drop, "p", 0.0) == 0.0):
-        out = torch.addmm(res.reshape(-1, res.shape[-1]), o.reshape(-1, o.shape[-1]), weight.t()).view(res.shape)
+        if kwargs.get(RESIDUAL_INPLACE_KW, False) and res.is_contiguous():
+            # the caller owns `res` (an intermediate of its own): accumulate in place, cuBLAS reads and writes C once
+            # (out of place, ATen first copies the residual into the output: a full extra read + write pass)
+            out = res.view(-1, res.shape[-1]).addmm_(o.reshape(-1, o.shape[-1]), weight.t()).view(res.shape)
+        else:
+            out = torch.addmm(res.reshape(-1, res.shape[-1]), o.reshape(-1, o.shape[-1]), weight.t()).view(res.shape)
         proc.deferred_bias = bias
         proc.fused_residual = True
         return out
