@@ -237,3 +237,60 @@ def test_unet_channels_last_equals_nchw_fast_path():
     cos = {k: F.cosine_similarity(v.flatten(), ref.flatten(), dim=0).item() for k, v in outs.items()}
     assert cos[True] >= 0.999 and cos[False] >= 0.999, cos
     assert cos[True] >= cos[False] - 3e-4, cos
+
+
+# ---- deferred-bias / fused-residual building blocks ------------------------------------------------------------
+@pytest.mark.parametrize("C", [320, 1280])
+def test_layernorm_pre_bias(C):
+    N, Fr = 19, 16
+    x, pre = _rand((N, Fr, C), 11, 2.0, 0.5), _rand((C,), 12, 0.5)
+    w, b = _rand((C,), 13, 0.3, 1.0), _rand((C,), 14, 0.3)
+    xs = (x.float() + pre.float()).to(torch.bfloat16).float()           # the reference's separate add rounds to bf16
+    ref = F.layer_norm(xs, (C,), w.float(), b.float(), 1e-5)
+    y = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5, None, pre.to(DEV)).float().cpu()
+    assert (y - ref).abs().max().item() <= 3e-2
+
+
+def test_geglu_ones_column():
+    rows, D = 77, 1280
+    x = _rand((rows, 2 * D), 15, 1.5)
+    y = ops.geglu(x.to(DEV), ones_column=True).cpu()
+    assert y.shape == (rows, D + 8)
+    assert torch.equal(y[:, :D], ops.geglu(x.to(DEV)).cpu())
+    pad = torch.zeros(rows, 8, dtype=torch.bfloat16)
+    pad[:, 0] = 1
+    assert torch.equal(y[:, D:], pad)
+
+
+def test_nhwc_add_with_bias():
+    N, C, h, w_ = 3, 640, 8, 8
+    x, y, b = _rand((N, C, h, w_), 16), _rand((N, C, h, w_), 17), _rand((C,), 18)
+    cl = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    out = ops.nhwc_add(cl(x), cl(y), b.to(DEV))
+    ref = (y.float() + b.float()[None, :, None, None]).to(torch.bfloat16).float() + x.float()
+    assert ops.is_channels_last(out)
+    assert (out.float().cpu() - ref).abs().max().item() <= 4e-2     # one bf16 rounding of a sum of magnitude <= 8
+    out0 = ops.nhwc_add(cl(x), cl(y))
+    assert (out0.float().cpu() - (x.float() + y.float())).abs().max().item() <= 4e-2
+
+
+def test_fused_residual_block_equals_separate_adds():
+    """Residual adds riding in the output GEMMs (deferred biases) against the same block with processors only."""
+    torch.manual_seed(3)
+    m = TransformerTemporalModel(num_attention_heads=8, attention_head_dim=40, in_channels=320, norm_num_groups=32,
+                                 positional_embeddings="sinusoidal", num_positional_embeddings=32).eval()
+    randomize_zero_init(m)
+    for p in m.parameters():      # non-zero biases everywhere, so a dropped or doubled bias cannot hide
+        if p.dim() == 1:
+            torch.nn.init.normal_(p, 0.0, 0.5)
+    x = torch.randn(2 * 16, 320, 8, 8)
+    m = m.to(DEV, torch.bfloat16)
+    outs = {}
+    for fast in (False, True):
+        handle = install(m, fast_path=fast)
+        with torch.no_grad():
+            outs[fast] = m(x.to(DEV, torch.bfloat16), num_frames=16)[0].float().cpu()
+        handle.uninstall()
+    cos = F.cosine_similarity(outs[True].flatten(), outs[False].flatten(), dim=0).item()
+    assert cos >= 0.9995, cos
+    assert (outs[True] - outs[False]).abs().max().item() <= 0.15 * outs[False].abs().max().item()
