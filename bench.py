@@ -39,8 +39,8 @@ SD15 = dict(block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, cross
 IMAGE_EMBED_DIM = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/r01_dense_attn_l0.md, profiles/r01_temporal_attn_l0.md); null until a capture exists
-TRAFFIC_DENSE_L0_BYTES = 565.8e6
-TRAFFIC_TEMPORAL_L0_BYTES = 312.1e6
+TRAFFIC_DENSE_L0_BYTES = 601.9e6
+TRAFFIC_TEMPORAL_L0_BYTES = 312.7e6
 
 
 def _peaks():
@@ -105,21 +105,66 @@ def make_inputs(videos, frames, latent, seed, dtype, device="cpu", pin=False):
 # clocks
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons DURING the timed region.  In-process NVML polling every 5 ms (the timed
+    region of a graph-replayed run is a few hundred ms: an `nvidia-smi -lms` child does not even start in that time);
+    `nvidia-smi` remains the fallback when the NVML binding is unavailable."""
+
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                   (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []      # (sm_mhz, power_w, reason_mask) from NVML
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.how = None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:  # noqa: BLE001
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+
+    def _poll(self, pynvml, handle):
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)),
+                                     pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0, int(reasons_fn(handle))))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
+        try:
+            pynvml, handle = self._nvml_handle()
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, args=(pynvml, handle), daemon=True)
+            self._thread.start()
+            self.how = "nvml"
+            return
+        except Exception:  # noqa: BLE001
+            self._thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            self.how = "nvidia-smi"
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -128,6 +173,17 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            sm = [s[0] for s in self.samples]
+            mask = 0
+            for s in self.samples:
+                mask |= s[2]
+            reasons = sorted(name for bit, name in self.REASON_BITS if mask & bit)
+            return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=self.sm_max,
+                        power_w_max=max((s[1] for s in self.samples), default=None), samples=len(sm), reasons=reasons,
+                        source="nvml, 5 ms period, timed region only")
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -144,7 +200,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons))
+                    power_w_max=max(power) if power else None, samples=len(sm), reasons=sorted(reasons),
+                    source="nvidia-smi -lms 100")
 
 
 # ------------------------------------------------------------------------------------------------------------

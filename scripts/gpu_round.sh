@@ -1,10 +1,11 @@
 #!/bin/bash
-# Developer helper run under gpurun: GPU tests, bench, ncu launch list and full captures of the two hot kernels.
+# Developer helper run under gpurun: GPU tests, bench, ncu launch list and full captures of the three attention kernels.
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log ) 
+( timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log )
 ( timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err )
-timeout 300 python scripts/profile_step.py > gpurun_out/step_profile.log 2>&1
+( timeout 300 python bench.py --steps 5 --warmup 3 --eager --no-cpu-baseline > gpurun_out/bench_eager.log 2>> gpurun_out/bench.err )
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --eager --profiler-range > gpurun_out/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:dense_attn -s 2 -c 2 -o gpurun_out/prof_dense -f python scripts/gpu_selftest.py --run perfdense > gpurun_out/ncu_dense.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:dense_attn_pipe -s 2 -c 1 -o gpurun_out/prof_dense -f python scripts/perf_aug.py > gpurun_out/ncu_dense.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:temporal_attn -s 2 -c 2 -o gpurun_out/prof_temporal -f python scripts/gpu_selftest.py --run perftemporal > gpurun_out/ncu_temporal.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.log; tail -3 gpurun_out/bench.err; head -3 gpurun_out/step_profile.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ip_xattn -s 2 -c 1 -o gpurun_out/prof_ip -f python scripts/perf_ip_one.py > gpurun_out/ncu_ip.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.log; tail -3 gpurun_out/bench.err

@@ -78,14 +78,25 @@ def main():
             f.write(f"| {v:.3f} | {v / T * 100:.1f} % | {cnt[k]} | `{k[:150]}` |\n")
     d_txt, d = ncu_digest(os.path.join(SRC, "prof_dense.ncu-rep"), f"Dense attention kernel, level 0 ({TAG})",
                           "Fused spatial self-attention + I2V-Adapter cross-frame attention of one level-0 block at the C2 size "
-                          "(32 frames x 8 heads x S=4096 x d=40, two problems, 1.374 TFLOP algorithmic per launch), launched by "
-                          "`scripts/gpu_selftest.py --run perfdense`.  Expected before measuring: exponential-bound "
-                          "(MUFU.EX2 16/clk/SM -> 1024 clk per 128x128 score tile vs 384 clk of MMA) -> XU busy, tensor pipe ~30 %, "
+                          "(32 frames x 8 heads x S=4096 x d=40, two problems, 1.374 TFLOP algorithmic per launch) on the "
+                          "augmented operand layout, launched by `scripts/perf_aug.py`.  Expected before measuring: "
+                          "exponential-bound (MUFU.EX2 16/clk/SM -> 1024 clk per 128x128 score tile vs 384 clk of MMA; 3 of 8 "
+                          "column pairs on the FMA-pipe polynomial) -> XU and FMA pipes both busy, tensor pipe ~30 %, "
                           "DRAM << peak (K/V re-reads served by L2).")
     t_txt, t = ncu_digest(os.path.join(SRC, "prof_temporal.ncu-rep"), f"Temporal attention kernel, level 0 ({TAG})",
                           "Motion-module temporal self-attention at the C2 level-0 size (8192 positions x 16 frames x 8 heads x "
                           "d=40, 335.5 MB algorithmic bytes per launch), launched by `scripts/gpu_selftest.py --run perftemporal`.  "
                           "Expected before measuring: HBM-bound, DRAM traffic ~ algorithmic bytes, tensor/ALU pipes mostly idle.")
+    ip_rep = os.path.join(SRC, "prof_ip.ncu-rep")
+    if os.path.exists(ip_rep):
+        i_txt, i = ncu_digest(ip_rep, f"IP-Adapter cross-attention kernel, level 0 ({TAG})",
+                              "Decoupled text (77) + image (4) cross-attention at the C2 level-0 size (32 frames x 4096 "
+                              "queries x 8 heads x d=40; reads Q and writes O once: 167.8 MB algorithmic bytes per launch), "
+                              "launched by `scripts/perf_ip_one.py`.  Expected before measuring: HBM-bound by design, in "
+                              "practice limited by the instruction count of the two-segment softmax at 2-3 resident warps "
+                              "per sub-partition.")
+        open(os.path.join(OUT, f"{TAG}_ip_attn_l0.md"), "w").write(i_txt)
+        print("ip:", i.get("gpu__time_duration.sum"), "dram r/w", i.get("dram__bytes_read.sum"), i.get("dram__bytes_write.sum"))
     open(os.path.join(OUT, f"{TAG}_dense_attn_l0.md"), "w").write(d_txt)
     open(os.path.join(OUT, f"{TAG}_temporal_attn_l0.md"), "w").write(t_txt)
     bench = open(os.path.join(SRC, "bench.log")).read().strip().splitlines()[-1]
