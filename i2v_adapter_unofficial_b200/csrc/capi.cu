@@ -711,15 +711,17 @@ int i2v_layernorm_pre_fwd(const void* x, const void* pre, const void* w, const v
   if (rc) return rc;
   const int nvec = C / 8;
   const int maxv = (nvec + 31) / 32;
-  const long long blocks = (rows + 7) / 8;
-  if (blocks > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "layernorm: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
   const uint4 *xv = (const uint4*)x, *wv = (const uint4*)w, *bv = (const uint4*)b, *pv = (const uint4*)pe, *prv = (const uint4*)pre;
   uint4* yv = (uint4*)y;
-  if (maxv <= 2)      i2v::layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
-  else if (maxv <= 3) i2v::layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
-  else if (maxv <= 5) i2v::layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
-  else                i2v::layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
+  // rows per warp: as many as keep the row cache at <= 8 vectors per lane
+  const int rpw = maxv <= 2 ? 4 : maxv <= 3 ? 2 : 1;
+  const long long blocks = (rows + 8 * rpw - 1) / (8 * rpw);
+  if (blocks > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "layernorm: too many rows");
+  if (maxv <= 2)      i2v::layernorm_kernel<2, 4><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
+  else if (maxv <= 3) i2v::layernorm_kernel<3, 2><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
+  else if (maxv <= 5) i2v::layernorm_kernel<5, 1><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
+  else                i2v::layernorm_kernel<8, 1><<<(unsigned)blocks, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, nvec, eps, prv);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

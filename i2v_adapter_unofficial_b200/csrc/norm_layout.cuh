@@ -34,79 +34,94 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   y[r, :] = (x[r, :] - mean) * rstd * w + b  (+ pe[r % pe_rows, :]),   x := x + pre (per channel) when pre != null
 // (the sum is rounded to bf16 first, as the reference's separate add would).  One warp per row, the row cached in registers (two-pass variance), MAXV 16-byte vectors per lane.
 // ---------------------------------------------------------------------------------------------------------------
-template <int MAXV>
+template <int MAXV, int R>
 __global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                         const uint4* __restrict__ w, const uint4* __restrict__ b,
                                                         const uint4* __restrict__ pe, int pe_rows, long long rows,
                                                         int nvec /* C / 8 */, float eps,
                                                         const uint4* __restrict__ pre = nullptr) {
+  // Every warp owns R consecutive rows and issues the loads of all of them before the first reduction: with one row
+  // per warp (two 16-byte loads per lane at C = 320) the kernel ran at 44 % of the copy bandwidth, latency-bound.
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const uint4* xr = x + row * nvec;
-  uint4 v[MAXV];
-  float s = 0.f;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  uint4 v[R][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
-      v[i] = xr[c];
-      if (pre) {   // x + pre[c]: a per-channel term the producer left out (deferred output-projection biases)
-        const uint4 pv = pre[c];
-        v[i].x = bf16_pack(bf16_lo(v[i].x) + bf16_lo(pv.x), bf16_hi(v[i].x) + bf16_hi(pv.x));
-        v[i].y = bf16_pack(bf16_lo(v[i].y) + bf16_lo(pv.y), bf16_hi(v[i].y) + bf16_hi(pv.y));
-        v[i].z = bf16_pack(bf16_lo(v[i].z) + bf16_lo(pv.z), bf16_hi(v[i].z) + bf16_hi(pv.z));
-        v[i].w = bf16_pack(bf16_lo(v[i].w) + bf16_lo(pv.w), bf16_hi(v[i].w) + bf16_hi(pv.w));
-      }
-      s += bf16_lo(v[i].x) + bf16_hi(v[i].x) + bf16_lo(v[i].y) + bf16_hi(v[i].y) + bf16_lo(v[i].z) + bf16_hi(v[i].z) +
-           bf16_lo(v[i].w) + bf16_hi(v[i].w);
+  for (int r = 0; r < R; ++r) {
+    const bool live = row0 + r < rows;
+    const uint4* xr = x + (row0 + r) * nvec;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      v[r][i] = (live && c < nvec) ? xr[c] : make_uint4(0u, 0u, 0u, 0u);
     }
   }
   const float inv_n = 1.f / (float)(nvec * 8);
-  const float mean = warp_sum(s) * inv_n;
-  float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
-      const uint32_t ww[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+    if (row >= rows) break;
+    float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = bf16_lo(ww[k]) - mean, bb = bf16_hi(ww[k]) - mean;
-        q += a * a + bb * bb;
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        if (pre) {   // x + pre[c]: a per-channel term the producer left out (deferred output-projection biases)
+          const uint4 pv = pre[c];
+          v[r][i].x = bf16_pack(bf16_lo(v[r][i].x) + bf16_lo(pv.x), bf16_hi(v[r][i].x) + bf16_hi(pv.x));
+          v[r][i].y = bf16_pack(bf16_lo(v[r][i].y) + bf16_lo(pv.y), bf16_hi(v[r][i].y) + bf16_hi(pv.y));
+          v[r][i].z = bf16_pack(bf16_lo(v[r][i].z) + bf16_lo(pv.z), bf16_hi(v[r][i].z) + bf16_hi(pv.z));
+          v[r][i].w = bf16_pack(bf16_lo(v[r][i].w) + bf16_lo(pv.w), bf16_hi(v[r][i].w) + bf16_hi(pv.w));
+        }
+        s += bf16_lo(v[r][i].x) + bf16_hi(v[r][i].x) + bf16_lo(v[r][i].y) + bf16_hi(v[r][i].y) + bf16_lo(v[r][i].z) +
+             bf16_hi(v[r][i].z) + bf16_lo(v[r][i].w) + bf16_hi(v[r][i].w);
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
-  uint4* yr = y + row * nvec;
-  const uint4* per = pe ? pe + (row % pe_rows) * nvec : nullptr;
+    const float mean = warp_sum(s) * inv_n;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
-      const uint4 wv = w[c], bv = b[c];
-      const uint32_t xin[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      const uint32_t win[4] = {wv.x, wv.y, wv.z, wv.w};
-      const uint32_t bin[4] = {bv.x, bv.y, bv.z, bv.w};
-      uint32_t pin[4] = {0u, 0u, 0u, 0u};
-      if (per) {
-        const uint4 pv = per[c];
-        pin[0] = pv.x; pin[1] = pv.y; pin[2] = pv.z; pin[3] = pv.w;
-      }
-      uint32_t out[4];
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const uint32_t ww[4] = {v[r][i].x, v[r][i].y, v[r][i].z, v[r][i].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        // LayerNorm result is rounded to bf16 before the embedding is added, as in the two-op reference sequence
-        float lo = (bf16_lo(xin[k]) - mean) * rstd * bf16_lo(win[k]) + bf16_lo(bin[k]);
-        float hi = (bf16_hi(xin[k]) - mean) * rstd * bf16_hi(win[k]) + bf16_hi(bin[k]);
-        if (per) {
-          const uint32_t r = bf16_pack(lo, hi);
-          lo = bf16_lo(r) + bf16_lo(pin[k]);
-          hi = bf16_hi(r) + bf16_hi(pin[k]);
+        for (int k = 0; k < 4; ++k) {
+          const float a = bf16_lo(ww[k]) - mean, bb = bf16_hi(ww[k]) - mean;
+          q += a * a + bb * bb;
         }
-        out[k] = bf16_pack(lo, hi);
       }
-      yr[c] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+    uint4* yr = y + row * nvec;
+    const uint4* per = pe ? pe + (row % pe_rows) * nvec : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const uint4 wv = w[c], bv = b[c];
+        const uint32_t xin[4] = {v[r][i].x, v[r][i].y, v[r][i].z, v[r][i].w};
+        const uint32_t win[4] = {wv.x, wv.y, wv.z, wv.w};
+        const uint32_t bin[4] = {bv.x, bv.y, bv.z, bv.w};
+        uint32_t pin[4] = {0u, 0u, 0u, 0u};
+        if (per) {
+          const uint4 pv = per[c];
+          pin[0] = pv.x; pin[1] = pv.y; pin[2] = pv.z; pin[3] = pv.w;
+        }
+        uint32_t out[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // LayerNorm result is rounded to bf16 before the embedding is added, as in the two-op reference sequence
+          float lo = (bf16_lo(xin[k]) - mean) * rstd * bf16_lo(win[k]) + bf16_lo(bin[k]);
+          float hi = (bf16_hi(xin[k]) - mean) * rstd * bf16_hi(win[k]) + bf16_hi(bin[k]);
+          if (per) {
+            const uint32_t rr = bf16_pack(lo, hi);
+            lo = bf16_lo(rr) + bf16_lo(pin[k]);
+            hi = bf16_hi(rr) + bf16_hi(pin[k]);
+          }
+          out[k] = bf16_pack(lo, hi);
+        }
+        yr[c] = make_uint4(out[0], out[1], out[2], out[3]);
+      }
     }
   }
 }
@@ -433,16 +448,25 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const GnNhwcParams P
   }
   __syncthreads();
   const int VC = P.C / 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
   const bool has_add = P.add != nullptr;
-  for (int r = r0 + warp; r < r1; r += nwarps) {
-    const uint4* src = reinterpret_cast<const uint4*>(P.x + ((long long)n * P.S + r) * P.C);
-    const long long orow = P.perm ? (((long long)v * P.S + r) * P.fg + f) : ((long long)n * P.S + r);
-    uint4* dst = reinterpret_cast<uint4*>(P.out + orow * P.C);
-    for (int cv = lane; cv < VC; cv += 32) {
-      const uint4 xv = src[cv];
-      const uint32_t ww[4] = {xv.x, xv.y, xv.z, xv.w};
+  // flat index space (row, 16-byte vector) of the chunk, every thread keeps four vectors in flight
+  const int total = (r1 - r0) * VC;
+  const uint4* src = reinterpret_cast<const uint4*>(P.x + ((long long)n * P.S + r0) * P.C);
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+    uint4 xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e < total) xv[u] = src[e];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      if (e >= total) break;
+      const int r = r0 + e / VC, cv = e % VC;
+      const long long orow = P.perm ? (((long long)v * P.S + r) * P.fg + f) : ((long long)n * P.S + r);
+      const uint32_t ww[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -458,7 +482,7 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const GnNhwcParams P
         }
         o[k] = bf16_pack(a, b);
       }
-      dst[cv] = make_uint4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<uint4*>(P.out + orow * P.C)[cv] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
