@@ -178,13 +178,13 @@ int launch_dense_pipe_cfg(const i2v::DenseParams& Pin, cudaStream_t stream) {
   return 0;
 }
 
-template <int D, int HG, int MT, int NSTG, int MINB>
+template <int D, int HG, int MT, int NSTG, int MINB, int NTXT = 0, int NK = 0>
 int launch_ip_stream(const i2v::IpStreamParams& P, int sms, cudaStream_t stream) {
   using Cfg = i2v::IpStreamCfg<D, HG, MT, NSTG, MINB>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kern = i2v::ip_xattn_stream_kernel<D, HG, MT, NSTG, MINB>;
+  auto kern = i2v::ip_xattn_stream_kernel<D, HG, MT, NSTG, MINB, NTXT, NK>;
   if (!attr_set[dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[dev & 63] = true;
@@ -553,15 +553,20 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
       P.v_sb = v_txt->stride_b; P.v_ss = v_txt->stride_s; P.o_sb = o->stride_b; P.o_ss = o->stride_s;
       P.batch = batch; P.sq = sq; P.heads = heads; P.nk = n_txt + n_ip; P.n_txt = n_txt; P.kv_group = kv_group;
       P.scale_log2e = scale * 1.4426950408889634f; P.ip_scale = ip_scale;
+      const bool std77 = n_txt == 77 && n_ip == 4 && g_tuning[5] != 2;   // tuning key 5 = 2: runtime token counts
       if (d == 40) {
         if (cfgsel == 1) return launch_ip_stream<40, 8, 2, 3, 1>(P, di->sms, (cudaStream_t)stream);
         if (cfgsel == 2) return launch_ip_stream<40, 4, 1, 3, 2>(P, di->sms, (cudaStream_t)stream);
-        return launch_ip_stream<40, 2, 1, 3, 3>(P, di->sms, (cudaStream_t)stream);   // 3 CTAs per SM: 180 us at C2 level 0
+        // the pipeline's token counts (77 text + 4 image) get the instantiation with compile-time key classes
+        if (std77) return launch_ip_stream<40, 2, 1, 3, 3, 77, 81>(P, di->sms, (cudaStream_t)stream);
+        return launch_ip_stream<40, 2, 1, 3, 3>(P, di->sms, (cudaStream_t)stream);   // 3 CTAs per SM
       }
       if (d == 80) {
         if (cfgsel == 1) return launch_ip_stream<80, 4, 1, 3, 1>(P, di->sms, (cudaStream_t)stream);
+        if (std77) return launch_ip_stream<80, 2, 1, 2, 2, 77, 81>(P, di->sms, (cudaStream_t)stream);
         return launch_ip_stream<80, 2, 1, 2, 2>(P, di->sms, (cudaStream_t)stream);
       }
+      if (std77) return launch_ip_stream<160, 2, 1, 2, 1, 77, 81>(P, di->sms, (cudaStream_t)stream);
       return launch_ip_stream<160, 2, 1, 2, 1>(P, di->sms, (cudaStream_t)stream);
     }
     DenseSeg seg{q, k_txt, v_txt, o, kv_group};

@@ -49,7 +49,9 @@ struct IpStreamCfg {
   static_assert((SMEM_BYTES + 1024) * MINB <= 228 * 1024, "smem budget");
 };
 
-template <int D, int HG, int MT, int NSTG, int MINB>
+// NTXT / NK > 0 fix the token counts at compile time (77 text + 4 image tokens is what the pipeline feeds): the key-tile
+// classification below then folds away; 0 = read them from the launch parameters.
+template <int D, int HG, int MT, int NSTG, int MINB, int NTXT = 0, int NK = 0>
 __global__ void __launch_bounds__(kIpThreads, MINB) ip_xattn_stream_kernel(const IpStreamParams P) {
   using Cfg = IpStreamCfg<D, HG, MT, NSTG, MINB>;
   constexpr int PITCH = Cfg::PITCH, KT = kIpKeys / 8, KP = kIpKeys / 16, ROWS = Cfg::ROWS;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(kIpThreads, MINB) ip_xattn_stream_kernel(const
         // ---- two softmaxes per row (rows g and g+8 of the m-tile live in this quad) ----
         // Key tiles are classified once (warp-uniform, from the launch parameters): entirely text, entirely image,
         // entirely padding, or mixed -- only the mixed ones (two of twelve at 77 + 4 tokens) pay per-element tests.
-        const int n_txt = P.n_txt, nk = P.nk;
+        const int n_txt = NTXT > 0 ? NTXT : P.n_txt, nk = NK > 0 ? NK : P.nk;
         auto cls = [&](int nt) { return (nt * 8 + 8 <= n_txt) ? 0 : (nt * 8 >= nk) ? 3 : (nt * 8 >= n_txt && nt * 8 + 8 <= nk) ? 1 : 2; };
         uint32_t pa[KT][2];
 #pragma unroll
@@ -241,8 +243,8 @@ __global__ void __launch_bounds__(kIpThreads, MINB) ip_xattn_stream_kernel(const
           l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
           l2 += __shfl_xor_sync(0xffffffffu, l2, 1);
           l2 += __shfl_xor_sync(0xffffffffu, l2, 2);
-          const float w1 = l1 > 0.f ? 1.f / l1 : 0.f;
-          const float w2 = l2 > 0.f ? P.ip_scale / l2 : 0.f;
+          const float w1 = l1 > 0.f ? rcp_approx(l1) : 0.f;
+          const float w2 = l2 > 0.f ? P.ip_scale * rcp_approx(l2) : 0.f;
 #pragma unroll
           for (int nt = 0; nt < KT; ++nt) {
             const int k = cls(nt);

@@ -67,7 +67,7 @@ void run() {
   float* out; long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 8);
   printf("EMU %d/8 deg %d clamp %d max %d pre %d sum %d:", EMU, DEG, (int)CLAMP, (int)WITH_MAX, (int)PRE, (int)SUM);
-  for (int warps : {4, 8, 16}) {
+  for (int warps : {4, 8, 12, 16}) {
     cudaMemset(cyc, 0, 8);
     cudaFuncSetAttribute(k<EMU, DEG, CLAMP, WITH_MAX, PRE, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     k<EMU, DEG, CLAMP, WITH_MAX, PRE, SUM><<<148, warps * 32, warps * 32 * (BN + 4) * 4>>>(out, cyc, 0.228f, 0.f);
@@ -133,7 +133,7 @@ void run2() {
   float* out; long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 8);
   printf("k2 EMU %d/8 mufu %d sum %d pack %d scale %d:", EMU, (int)MUFU_ON, (int)SUM, (int)PACK, (int)SCALE);
-  for (int warps : {4, 8, 16}) {
+  for (int warps : {4, 8, 12, 16}) {
     cudaMemset(cyc, 0, 8);
     k2<EMU, MUFU_ON, SUM, PACK, SCALE><<<148, warps * 32>>>(out, cyc, 0.228f, 0.f);
     cudaError_t e = cudaDeviceSynchronize();

@@ -1,5 +1,5 @@
 """Developer tool: IP-Adapter cross-attention (K3) at the C2 level shapes: streaming kernel vs the tcgen05 single-tile
-kernel (tuning key 5 = 1), achieved GB/s on the algorithmic bytes (read Q, write O once)."""
+kernel (tuning key 5 = 1; key 5 = 2: streaming kernel with run-time token counts), achieved GB/s on the algorithmic bytes (read Q, write O once)."""
 import os
 import sys
 
@@ -17,7 +17,7 @@ for (B, S, d) in [(32, 4096, 40), (32, 1024, 80), (32, 256, 160), (32, 64, 160)]
     k, v = kv[:, :, 0], kv[:, :, 1]
     nbytes = 2 * q.numel() * 2
     res = {}
-    for name, key, cfg in (("stream", 0, 0), ("stream-1", 0, 1), ("stream-2", 0, 2), ("tcgen05", 1, 0)):
+    for name, key, cfg in (("stream", 0, 0), ("stream-rt", 2, 0), ("stream-1", 0, 1), ("stream-2", 0, 2), ("tcgen05", 1, 0)):
         lib.i2v_set_tuning(5, key)
         lib.i2v_set_tuning(6, cfg)
         for _ in range(3):
