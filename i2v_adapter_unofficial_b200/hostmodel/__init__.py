@@ -5,7 +5,8 @@ from .ddim import DDIMScheduler  # noqa: F401
 from .i2v_adapter import I2VAdapterModule, I2VAdapterTransformer2DModel, I2VAdapterTransformerBlock  # noqa: F401
 from .layers import BasicTransformerBlock, ImageProjection  # noqa: F401
 from .pipeline import denoise, denoise_step  # noqa: F401
-from .temporal import DownBlockMotion, TransformerTemporalModel, UpBlockMotion  # noqa: F401
+from .checkpoint import load_ip_adapter_file, save_ip_adapter_file  # noqa: F401
+from .temporal import DownBlockMotion, MotionAdapter, MotionModules, TransformerTemporalModel, UpBlockMotion  # noqa: F401
 from .unet import (  # noqa: F401
     CrossFrameAttnDownBlockMotion,
     CrossFrameAttnUpBlockMotion,

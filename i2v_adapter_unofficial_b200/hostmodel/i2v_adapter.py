@@ -17,6 +17,7 @@ from typing import Any, Dict, Optional
 import torch
 from torch import nn
 
+from . import checkpoint
 from .attention import Attention
 from .layers import BasicTransformerBlock
 
@@ -204,3 +205,25 @@ class I2VAdapterModule(nn.Module):
 
     def forward(self):  # pragma: no cover - container only
         pass
+
+    # ---- on-disk format of the trained adapter (diffusers ModelMixin layout; reference call sites
+    # src/pipelines/pipeline_i2v_adapter.py:740, src/models/unet_motion_cross_frame_attn.py:1080-1097) ----
+    def save_pretrained(self, save_directory: str, is_main_process: bool = True, safe_serialization: bool = True,
+                        variant: Optional[str] = None, push_to_hub: bool = False, **_unused) -> None:
+        if push_to_hub:
+            raise ValueError("push_to_hub is not available: this environment has no network")
+        if is_main_process:
+            checkpoint.save_model_directory(self, self.config, "I2VAdapterModule", save_directory, safe_serialization,
+                                            variant)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype: Optional[torch.dtype] = None,
+                        variant: Optional[str] = None, **_unused) -> "I2VAdapterModule":
+        config, state = checkpoint.load_model_directory(pretrained_model_name_or_path, variant)
+        module = cls(**checkpoint.constructor_kwargs(
+            config, ("block_depth", "block_out_channels", "num_attention_heads", "transformer_layers_per_block",
+                     "mid_block_depth")))
+        module.load_state_dict(state)   # strict, as ModelMixin: missing / unexpected keys are an error
+        if torch_dtype is not None:
+            module.to(torch_dtype)
+        return module.eval()

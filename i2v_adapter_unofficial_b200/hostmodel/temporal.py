@@ -131,3 +131,70 @@ class UpBlockMotion(nn.Module):
             for u in self.upsamplers:
                 hidden_states = u(hidden_states, upsample_size)
         return hidden_states
+
+
+class MotionModules(nn.Module):
+    """``layers_per_block`` temporal transformers of one resolution (diffusers ``unet_motion_model.MotionModules``)."""
+
+    def __init__(self, in_channels: int, layers_per_block: int = 2, num_attention_heads: int = 8,
+                 norm_num_groups: int = 32, max_seq_length: int = 32):
+        super().__init__()
+        self.motion_modules = nn.ModuleList(
+            [_motion_module(in_channels, num_attention_heads, norm_num_groups, max_seq_length)
+             for _ in range(layers_per_block)])
+
+
+class MotionAdapter(nn.Module):
+    """Weights-only container of the AnimateDiff motion modules with the UNet's key layout
+    (``{down,up}_blocks.N.motion_modules.M.*``, ``mid_block.motion_modules.M.*``): the diffusers ``MotionAdapter`` the
+    reference loads with ``from_pretrained`` (``src/pipelines/pipeline_i2v_adapter.py:733,745``) and rebuilds in
+    ``obtain_motion_modules`` (``src/models/unet_motion_cross_frame_attn.py:1060-1078``)."""
+
+    def __init__(self, block_out_channels=(320, 640, 1280, 1280), motion_layers_per_block: int = 2,
+                 motion_mid_block_layers_per_block: int = 1, motion_num_attention_heads: int = 8,
+                 motion_norm_num_groups: int = 32, motion_max_seq_length: int = 32, use_motion_mid_block: bool = True,
+                 conv_in_channels: Optional[int] = None):
+        super().__init__()
+        self.config = dict(block_out_channels=tuple(block_out_channels), motion_layers_per_block=motion_layers_per_block,
+                           motion_mid_block_layers_per_block=motion_mid_block_layers_per_block,
+                           motion_num_attention_heads=motion_num_attention_heads,
+                           motion_norm_num_groups=motion_norm_num_groups, motion_max_seq_length=motion_max_seq_length,
+                           use_motion_mid_block=use_motion_mid_block, conv_in_channels=conv_in_channels)
+        if conv_in_channels is not None:
+            raise ValueError("conv_in_channels (PIA) is not part of the SD1.5 motion adapter this mirror covers")
+
+        def mods(ch, layers):
+            return MotionModules(ch, layers, motion_num_attention_heads, motion_norm_num_groups, motion_max_seq_length)
+
+        self.down_blocks = nn.ModuleList([mods(c, motion_layers_per_block) for c in block_out_channels])
+        self.mid_block = (mods(block_out_channels[-1], motion_mid_block_layers_per_block)
+                          if use_motion_mid_block else None)
+        self.up_blocks = nn.ModuleList([mods(c, motion_layers_per_block + 1) for c in reversed(block_out_channels)])
+
+    def forward(self, sample):  # pragma: no cover - container only
+        pass
+
+    def save_pretrained(self, save_directory: str, is_main_process: bool = True, safe_serialization: bool = True,
+                        variant: Optional[str] = None, push_to_hub: bool = False, **_unused) -> None:
+        from . import checkpoint
+
+        if push_to_hub:
+            raise ValueError("push_to_hub is not available: this environment has no network")
+        if is_main_process:
+            checkpoint.save_model_directory(self, self.config, "MotionAdapter", save_directory, safe_serialization,
+                                            variant)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, torch_dtype: Optional[torch.dtype] = None,
+                        variant: Optional[str] = None, **_unused) -> "MotionAdapter":
+        from . import checkpoint
+
+        config, state = checkpoint.load_model_directory(pretrained_model_name_or_path, variant)
+        module = cls(**checkpoint.constructor_kwargs(
+            config, ("block_out_channels", "motion_layers_per_block", "motion_mid_block_layers_per_block",
+                     "motion_num_attention_heads", "motion_norm_num_groups", "motion_max_seq_length",
+                     "use_motion_mid_block", "conv_in_channels")))
+        module.load_state_dict(state)
+        if torch_dtype is not None:
+            module.to(torch_dtype)
+        return module.eval()

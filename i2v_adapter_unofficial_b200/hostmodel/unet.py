@@ -13,10 +13,11 @@ from typing import Any, Dict, Optional, Tuple, Union
 import torch
 from torch import nn
 
+from . import checkpoint
 from .attention import AttnProcessor2_0, IPAdapterAttnProcessor2_0
 from .i2v_adapter import I2VAdapterModule, I2VAdapterTransformer2DModel, _Sample
 from .layers import Downsample2D, ImageProjection, ResnetBlock2D, TimestepEmbedding, Timesteps, Upsample2D
-from .temporal import DownBlockMotion, UpBlockMotion, _motion_module
+from .temporal import DownBlockMotion, MotionAdapter, UpBlockMotion, _motion_module
 
 
 def _spatial_transformer(channels, heads, cross_dim, groups, use_linear_projection=False, only_cross_attention=False,
@@ -326,6 +327,49 @@ class UNetMotionCrossFrameAttnModel(nn.Module):
         module = I2VAdapterModule(self.layers_per_block, self.config.block_out_channels, heads)
         module.load_state_dict(sd)
         return module
+
+    def load_motion_modules(self, motion_adapter: Optional[MotionAdapter]) -> None:
+        """Reference :1028-1036."""
+        for i, down_block in enumerate(motion_adapter.down_blocks):
+            self.down_blocks[i].motion_modules.load_state_dict(down_block.motion_modules.state_dict())
+        for i, up_block in enumerate(motion_adapter.up_blocks):
+            self.up_blocks[i].motion_modules.load_state_dict(up_block.motion_modules.state_dict())
+        # to support older motion modules that don't have a mid_block
+        if hasattr(self.mid_block, "motion_modules") and motion_adapter.mid_block is not None:
+            self.mid_block.motion_modules.load_state_dict(motion_adapter.mid_block.motion_modules.state_dict())
+
+    def obtain_motion_modules(self) -> MotionAdapter:
+        """Reference :1060-1078."""
+        sd = {k: v for k, v in self.state_dict().items() if "motion_modules" in k}
+        adapter = MotionAdapter(
+            block_out_channels=self.config["block_out_channels"],
+            motion_layers_per_block=self.config["layers_per_block"],
+            motion_norm_num_groups=self.config["norm_num_groups"],
+            motion_num_attention_heads=self.config["motion_num_attention_heads"],
+            motion_max_seq_length=self.config["motion_max_seq_length"],
+            use_motion_mid_block=bool(self.config["use_motion_mid_block"]))
+        adapter.load_state_dict(sd)
+        return adapter
+
+    def save_i2v_adapter_modules(self, save_directory: str, is_main_process: bool = True,
+                                 safe_serialization: bool = True, variant: Optional[str] = None,
+                                 push_to_hub: bool = False, **kwargs) -> None:
+        """Reference :1080-1097."""
+        self.obtain_i2v_adapter_modules().save_pretrained(
+            save_directory=save_directory, is_main_process=is_main_process, safe_serialization=safe_serialization,
+            variant=variant, push_to_hub=push_to_hub, **kwargs)
+
+    def save_motion_modules(self, save_directory: str, is_main_process: bool = True, safe_serialization: bool = True,
+                            variant: Optional[str] = None, push_to_hub: bool = False, **kwargs) -> None:
+        """Reference :1099-1116."""
+        self.obtain_motion_modules().save_pretrained(
+            save_directory=save_directory, is_main_process=is_main_process, safe_serialization=safe_serialization,
+            variant=variant, push_to_hub=push_to_hub, **kwargs)
+
+    def load_ip_adapter(self, weights_path: str) -> None:
+        """``ip-adapter_sd15.bin`` / ``.safetensors`` -> IP-Adapter processors + image projection (what the pipeline's
+        ``load_ip_adapter`` ends up calling: ``_load_ip_adapter_weights``, reference :1230-1287)."""
+        self._load_ip_adapter_weights(checkpoint.load_ip_adapter_file(weights_path))
 
     def freeze_unet_params(self, freeze_animatediff: bool = True) -> None:
         for p in self.parameters():

@@ -294,3 +294,36 @@ def test_fused_residual_block_equals_separate_adds():
     cos = F.cosine_similarity(outs[True].flatten(), outs[False].flatten(), dim=0).item()
     assert cos >= 0.9995, cos
     assert (outs[True] - outs[False]).abs().max().item() <= 0.15 * outs[False].abs().max().item()
+
+
+def test_adapter_checkpoints_loaded_after_install_take_effect(tmp_path):
+    """Weights read from disk (I2V-Adapter / motion-adapter directories, reference load_i2v_adapter :1038-1041 and
+    load_motion_modules :1028-1036) into a UNet whose B200 processors and fast path are already installed: the packed
+    projection weights are caches keyed on the parameters' version and must follow."""
+    from i2v_adapter_unofficial_b200.hostmodel import I2VAdapterModule, MotionAdapter
+
+    trained = randomize_zero_init(make_unet(SD15_HEADDIM_CFG, seed=11))
+    trained.save_i2v_adapter_modules(str(tmp_path / "i2v"))
+    trained.save_motion_modules(str(tmp_path / "motion"))
+    sample, ctx, _ = unet_inputs(trained, videos=1, frames=4, size=16, tokens=77)
+
+    def run(u):
+        with torch.no_grad():
+            return u(sample.to(DEV, torch.bfloat16), 37, True, ctx.to(DEV, torch.bfloat16)).sample.float().cpu()
+
+    trained = trained.to(DEV, torch.bfloat16)
+    install(trained)
+    want = run(trained)
+
+    other = randomize_zero_init(make_unet(SD15_HEADDIM_CFG, seed=11))
+    with torch.no_grad():
+        for name, p in other.named_parameters():
+            if "i2v_adapter" in name or "motion_modules" in name:
+                p.mul_(0.25)
+    other = other.to(DEV, torch.bfloat16)
+    install(other)
+    before = run(other)                       # builds every packed-weight cache from the perturbed weights
+    assert F.cosine_similarity(before.flatten(), want.flatten(), dim=0).item() < 0.999
+    other.load_i2v_adapter(I2VAdapterModule.from_pretrained(str(tmp_path / "i2v"), torch_dtype=torch.bfloat16))
+    other.load_motion_modules(MotionAdapter.from_pretrained(str(tmp_path / "motion"), torch_dtype=torch.bfloat16))
+    assert torch.equal(run(other), want)
