@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "i2v_layernorm_fwd",
     "i2v_layernorm_pre_fwd",
     "i2v_geglu_ld_fwd",
+    "i2v_ff_geglu_fwd",
     "i2v_geglu_fwd",
     "i2v_gn_stats",
     "i2v_gn_apply_transpose",
@@ -104,6 +105,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_layernorm_pre_fwd.argtypes = [p, p, p, p, p, p, ll, i, i, f, p]
     lib.i2v_geglu_ld_fwd.restype = i
     lib.i2v_geglu_ld_fwd.argtypes = [p, p, ll, i, i, p]
+    lib.i2v_ff_geglu_fwd.restype = i
+    lib.i2v_ff_geglu_fwd.argtypes = [p, p, p, p, ll, i, i, i, p]
     lib.i2v_gn_stats.restype = i
     lib.i2v_gn_stats.argtypes = [p, p, i, i, i, i, p]
     lib.i2v_gn_apply_transpose.restype = i

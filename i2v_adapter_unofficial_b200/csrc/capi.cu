@@ -14,6 +14,7 @@
 #include "generic_attn.cuh"
 #include "norm_layout.cuh"
 #include "temporal_attn.cuh"
+#include "ff_geglu_gemm_sm100.cuh"
 
 namespace {
 
@@ -749,6 +750,56 @@ int i2v_geglu_ld_fwd(const void* x, void* y, long long rows, int D, int ld_out, 
   long long blocks = (rows + 7) / 8;   // one warp per row, eight warps per CTA
   if (blocks > (long long)di->sms * 8) blocks = (long long)di->sms * 8;
   i2v::geglu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, rows, D / 8, ld_out / 8);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix: dims (cols, rows), box (64, 128), 128-byte swizzle.
+static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(I2V_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) for a [%lld, %d] matrix", (int)r, rows, cols);
+  return 0;
+}
+
+int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, long long rows, int K, int N, int ld_out,
+                     void* stream) {
+  if (rows <= 0 || K <= 0 || N <= 0) return fail(I2V_ERR_BAD_SHAPE, "ff_geglu: sizes must be positive");
+  if (K % 64 || N % 128)
+    return fail(I2V_ERR_UNSUPPORTED, "ff_geglu: needs K %% 64 == 0 and N %% 128 == 0 (K=%d N=%d)", K, N);
+  if (ld_out != N && ld_out != N + 8) return fail(I2V_ERR_BAD_SHAPE, "ff_geglu: ld_out (%d) must be N or N + 8 (N=%d)", ld_out, N);
+  if (!x || !w || !y) return fail(I2V_ERR_BAD_SHAPE, "ff_geglu: null pointer");
+  if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (bias && !aligned16(bias)))
+    return fail(I2V_ERR_MISALIGNED, "ff_geglu: pointers must be 16-byte aligned");
+  if (rows > 0x7fffffffLL) return fail(I2V_ERR_BAD_SHAPE, "ff_geglu: too many rows (%lld)", rows);
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if ((rc = get_encode_fn())) return rc;
+  i2v::FfGegluParams P;
+  memset(&P, 0, sizeof(P));
+  if ((rc = make_tmap_2d(&P.tm_x, x, rows, K))) return rc;
+  if ((rc = make_tmap_2d(&P.tm_w, w, 2LL * N, K))) return rc;
+  P.bias = (const __nv_bfloat16*)bias; P.out = (__nv_bfloat16*)y;
+  P.rows = rows; P.N = N; P.K = K; P.ld = ld_out;
+  P.m_tiles = (int)((rows + 127) / 128); P.n_tiles = N / 128;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(i2v::ff_geglu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kFfSmemBytes));
+    attr_set[dev & 63] = true;
+  }
+  const long long tiles = (long long)P.m_tiles * P.n_tiles;
+  const long long grid = tiles < di->sms ? tiles : di->sms;
+  i2v::ff_geglu_gemm_kernel<<<(unsigned)grid, i2v::kFfThreads, i2v::kFfSmemBytes, (cudaStream_t)stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -127,6 +127,16 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
         "r"(c2), "r"(c3), "l"(cache_hint)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
+                                            uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "l"(cache_hint)
+      : "memory");
+}
 // L2 eviction-priority policies (createpolicy encodings used by TMA cache hints).
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;

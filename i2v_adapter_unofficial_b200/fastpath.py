@@ -51,10 +51,21 @@ def _ln(x: torch.Tensor, norm: nn.LayerNorm, pe: Optional[torch.Tensor] = None,
     return ops.layernorm(x.contiguous(), norm.weight, norm.bias, norm.eps, pe, pre)
 
 
+FUSED_FF_GEGLU = True   # feed-forward input projection + GEGLU in one tcgen05 GEMM (i2v_ff_geglu_fwd) where its shapes fit
+
+
+def _geglu_proj(x: torch.Tensor, proj: nn.Linear, ones_column: bool) -> torch.Tensor:
+    """``hidden * gelu(gate)`` of ``proj(x).chunk(2, -1)`` (diffusers GEGLU; src/modules/i2v_adapter.py:535-561)."""
+    if FUSED_FF_GEGLU and ops.ff_geglu_supported(x, proj.weight) and x.is_contiguous() and \
+            (proj.bias is None or proj.bias.is_contiguous()):
+        return ops.ff_geglu(x, proj.weight, proj.bias, ones_column=ones_column)
+    return ops.geglu(F.linear(x, proj.weight, proj.bias), ones_column=ones_column)
+
+
 def _ff(ff: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """FeedForward with GEGLU: net.0.proj (Linear dim -> 8 dim), fused GEGLU, net.2 (Linear 4 dim -> dim)."""
     proj = ff.net[0].proj
-    h = ops.geglu(F.linear(x, proj.weight, proj.bias))
+    h = _geglu_proj(x, proj, False)
     out = ff.net[2]
     return F.linear(h, out.weight, out.bias)
 
@@ -191,7 +202,7 @@ def _block_forward_fast(self, hidden_states, encoder_hidden_states, enable_cross
         pending = b1 is not None or b2 is not None
         norm_h = _ln(hidden_states, self.norm3, None, p2 if pending else None)                    # :539
         proj = self.ff.net[0].proj
-        h = ops.geglu(F.linear(norm_h, proj.weight, proj.bias), ones_column=True)                 # [.., 4C + 8]
+        h = _geglu_proj(norm_h, proj, True)                                                       # [.., 4C + 8]
         C = hidden_states.shape[-1]
         if self.attn2 is not None:   # hidden_states is this block's own tensor (see above): accumulate in place
             hidden_states.view(-1, C).addmm_(h.view(-1, h.shape[-1]), w_aug.t())

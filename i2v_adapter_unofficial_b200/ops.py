@@ -269,6 +269,34 @@ def geglu(x: torch.Tensor, ones_column: bool = False) -> torch.Tensor:
     return y
 
 
+def ff_geglu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+             ones_column: bool = False) -> torch.Tensor:
+    """GEGLU feed-forward input projection fused with the activation: ``h, g = F.linear(x, weight, bias).chunk(2, -1);
+    h * gelu(g)`` in one tcgen05 GEMM (include/i2v_attn_b200.h, i2v_ff_geglu_fwd).  x [..., K], weight [2N, K],
+    bias [2N] -> [..., N] (or [..., N + 8] with the ones column of `geglu`)."""
+    dev = _require_bf16_contig(x)
+    K = x.shape[-1]
+    N = weight.shape[0] // 2
+    if weight.shape != (2 * N, K) or not weight.is_contiguous() or weight.dtype != torch.bfloat16:
+        raise ValueError(f"ff_geglu: weight must be a contiguous bf16 [2N, K] matrix, got {tuple(weight.shape)} {weight.dtype}")
+    if bias is not None and (bias.shape != (2 * N,) or bias.dtype != torch.bfloat16 or not bias.is_contiguous()):
+        raise ValueError("ff_geglu: bias must be a contiguous bf16 [2N] vector")
+    rows = x.numel() // K
+    ld = N + 8 if ones_column else N
+    y = torch.empty(x.shape[:-1] + (ld,), dtype=x.dtype, device=dev)
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_ff_geglu_fwd(x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+                                        y.data_ptr(), rows, K, N, ld, _stream(dev)))
+    return y
+
+
+def ff_geglu_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Shapes the fused kernel takes (K % 64 == 0, N % 128 == 0, bf16, contiguous)."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
+            and x.shape[-1] % 64 == 0 and (weight.shape[0] // 2) % 128 == 0 and weight.shape[0] % 2 == 0)
+
+
 def group_norm_tokens(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, eps: float,
                       frames_per_stat: int = 1) -> torch.Tensor:
     """GroupNorm of x [N, C, h, w] with statistics shared by ``frames_per_stat`` consecutive batch entries, written

@@ -144,6 +144,15 @@ int i2v_geglu_fwd(const void* x, void* y, long long rows, int D, void* stream);
 /* i2v_geglu_ld_fwd: y has row pitch ld_out = D or D + 8; with D + 8 the extra columns are (1, 0, .., 0): a ones column
  *   so that the following GEMM can carry its bias as one more weight column (and its residual as the beta = 1 term). */
 int i2v_geglu_ld_fwd(const void* x, void* y, long long rows, int D, int ld_out, void* stream);
+/* i2v_ff_geglu_fwd: the GEGLU feed-forward's input projection fused with the activation (diffusers FeedForward
+ *   net[0] = GEGLU(dim, 4 dim): proj = Linear(dim, 8 dim), hidden, gate = proj(x).chunk(2), hidden * gelu(gate);
+ *   reference call site src/modules/i2v_adapter.py:535-561):
+ *     y[r, c] = (x W[c]^T + bias[c]) * gelu(x W[N + c]^T + bias[N + c]),   c < N
+ *   x: [rows, K] bf16 row-major, w: [2N, K] (the nn.Linear weight as stored), bias: [2N] or NULL, y: [rows, ld_out] with
+ *   ld_out = N or N + 8 (ones column as in i2v_geglu_ld_fwd).  K % 64 == 0, N % 128 == 0.  One tcgen05 GEMM whose
+ *   accumulator tile pairs hidden and gate columns, so the [rows, 2N] projection never goes to HBM. */
+int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, long long rows, int K, int N, int ld_out,
+                     void* stream);
 /* GroupNorm + layout change in two passes over x [N, C, S] (NCHW, S = h*w), G groups, statistics shared by `fg`
  * consecutive batch entries (fg = 1: the spatial transformer's per-frame GroupNorm; fg = num_frames: the motion module's
  * GroupNorm over (C/G, F, h, w) per video, N = videos * fg, frame index fastest):

@@ -327,3 +327,35 @@ def test_adapter_checkpoints_loaded_after_install_take_effect(tmp_path):
     other.load_i2v_adapter(I2VAdapterModule.from_pretrained(str(tmp_path / "i2v"), torch_dtype=torch.bfloat16))
     other.load_motion_modules(MotionAdapter.from_pretrained(str(tmp_path / "motion"), torch_dtype=torch.bfloat16))
     assert torch.equal(run(other), want)
+
+
+# ---- feed-forward input projection fused with GEGLU (tcgen05 GEMM) ------------------------------------------------
+@pytest.mark.parametrize("case", [(256, 320, 1280, True), (1000, 64, 128, False), (384, 640, 2560, True),
+                                  (130, 1280, 5120, True), (5000, 320, 1280, False)],
+                         ids=lambda c: "rows{}K{}N{}bias{}".format(*c))
+@pytest.mark.parametrize("ones", [False, True])
+def test_ff_geglu_gemm_matches_fp32_reference(case, ones):
+    rows, K, N, with_bias = case
+    x = _rand((rows, K), 41, 1.0)
+    w = _rand((2 * N, K), 42, K ** -0.5)
+    b = _rand((2 * N,), 43, 0.5) if with_bias else None
+    proj = F.linear(x.float(), w.float(), None if b is None else b.float())
+    ref = proj[:, :N] * F.gelu(proj[:, N:])
+    y = ops.ff_geglu(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV), ones_column=ones).float().cpu()
+    assert y.shape == (rows, N + 8 if ones else N)
+    err = (y[:, :N] - ref).abs()
+    assert err.max().item() <= 2e-2 * max(1.0, ref.abs().max().item()), err.max().item()
+    assert (err / (ref.abs() + 0.1)).mean().item() <= 4e-3
+    if ones:
+        pad = torch.zeros(rows, 8)
+        pad[:, 0] = 1
+        assert torch.equal(y[:, N:], pad)
+
+
+def test_ff_geglu_rejects_unsupported_shapes():
+    x, w = _rand((64, 72), 44).to(DEV), _rand((256, 72), 45).to(DEV)
+    with pytest.raises(RuntimeError, match="K % 64"):
+        ops.ff_geglu(x, w)
+    x, w = _rand((64, 64), 46).to(DEV), _rand((192, 64), 47).to(DEV)
+    with pytest.raises(RuntimeError, match="N % 128"):
+        ops.ff_geglu(x, w)
