@@ -720,6 +720,17 @@ int i2v_layernorm_pre_fwd(const void* x, const void* pre, const void* w, const v
   cudaStream_t st = (cudaStream_t)stream;
   const uint4 *xv = (const uint4*)x, *wv = (const uint4*)w, *bv = (const uint4*)b, *pv = (const uint4*)pe, *prv = (const uint4*)pre;
   uint4* yv = (uint4*)y;
+  if ((nvec == 40 || nvec == 80 || nvec == 160) && g_tuning[7] != 3) {   // SD1.5 widths: five vectors per lane (tuning key 7 = 3: off)
+    const int lpr = nvec / 5, rows_per_warp = 32 / lpr;
+    long long nb = (rows + 8LL * rows_per_warp - 1) / (8LL * rows_per_warp);
+    if (nb > (long long)di->sms * 8) nb = (long long)di->sms * 8;   // persistent: eight CTAs of eight warps per SM
+    if (lpr == 8)       i2v::layernorm5_kernel<8><<<(unsigned)nb, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, eps, prv);
+    else if (lpr == 16) i2v::layernorm5_kernel<16><<<(unsigned)nb, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, eps, prv);
+    else                i2v::layernorm5_kernel<32><<<(unsigned)nb, 256, 0, st>>>(xv, yv, wv, bv, pv, pe_rows, rows, eps, prv);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+  }
   // rows per warp: as many as keep the row cache at <= 8 vectors per lane
   const int rpw = maxv <= 2 ? 4 : maxv <= 3 ? 2 : 1;
   const long long blocks = (rows + 8 * rpw - 1) / (8 * rpw);
@@ -791,15 +802,47 @@ int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, lo
   P.rows = rows; P.N = N; P.K = K; P.ld = ld_out;
   P.m_tiles = (int)((rows + 127) / 128); P.n_tiles = N / 128;
   static bool attr_set[64] = {false};
+  static int max_clusters[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(i2v::ff_geglu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kFfSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(i2v::ff_geglu_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kFfSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(i2v::ff_geglu_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kFfSmemBytes));
+    // how many 2-CTA clusters of this kernel the device can hold at once (persistent grid: one wave)
+    cudaLaunchConfig_t probe = {};
+    probe.gridDim = dim3((unsigned)(di->sms / 2 * 2));
+    probe.blockDim = dim3(i2v::kFfThreads);
+    probe.dynamicSmemBytes = i2v::kFfSmemBytes;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeClusterDimension;
+    pa[0].val.clusterDim.x = 2; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+    probe.attrs = pa; probe.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, i2v::ff_geglu_gemm_kernel<2>, &probe) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    max_clusters[dev & 63] = n;
     attr_set[dev & 63] = true;
   }
   const long long tiles = (long long)P.m_tiles * P.n_tiles;
-  const long long grid = tiles < di->sms ? tiles : di->sms;
-  i2v::ff_geglu_gemm_kernel<<<(unsigned)grid, i2v::kFfThreads, i2v::kFfSmemBytes, (cudaStream_t)stream>>>(P);
+  // tuning key 7: 1 = single-CTA kernel, 2 = clusters even where they are not the default
+  const int ncl = max_clusters[dev & 63] < di->sms / 2 ? max_clusters[dev & 63] : di->sms / 2;
+  const bool use_cluster = g_tuning[7] != 1 && ncl > 0 && P.m_tiles >= 2 && (K <= 640 || g_tuning[7] == 2);
+  if (use_cluster) {
+    const long long units = (long long)((P.m_tiles + 1) / 2) * P.n_tiles;
+    const long long clusters = units < ncl ? units : ncl;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(i2v::kFfThreads);
+    cfg.dynamicSmemBytes = i2v::kFfSmemBytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, i2v::ff_geglu_gemm_kernel<2>, P));
+  } else {
+    const long long grid = tiles < di->sms ? tiles : di->sms;
+    i2v::ff_geglu_gemm_kernel<1><<<(unsigned)grid, i2v::kFfThreads, i2v::kFfSmemBytes, (cudaStream_t)stream>>>(P);
+  }
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
@@ -909,7 +952,10 @@ int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, vo
   const int vg = (N / fg) * G;
   i2v::gn_finalize_kernel<<<(vg + 7) / 8, 256, 0, (cudaStream_t)stream>>>(P);   // one warp per (video, group)
   CUDA_TRY(cudaGetLastError());
-  i2v::gn_apply_rows_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(P);
+  // thread = (channel vector, row phase): as many row phases as fit 512 threads
+  const int rpp = VC >= 512 ? 1 : 512 / VC;
+  const int ablock = (VC * rpp + 31) / 32 * 32;
+  i2v::gn_apply_rows_kernel<<<grid, ablock, 0, (cudaStream_t)stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(3);
   return 0;

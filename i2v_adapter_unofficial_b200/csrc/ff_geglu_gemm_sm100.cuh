@@ -12,8 +12,14 @@
 // Persistent, warp-specialised: 1 TMA warp (x tile 128 x 64 and two 128 x 64 weight boxes -- hidden rows n0.. and gate
 // rows N + n0.. of the same nn.Linear weight, stacked into one 256-row K-major operand -- through a 4-stage ring), 1
 // MMA-issuing warp (tcgen05.mma M = 128, N = 256, K = 16; fp32 accumulators double-buffered in TMEM: 2 x 256
-// columns), 8 epilogue warps (lane quarter x column half) that overlap tile i's GELU with tile i+1's MMAs.
+// columns), 16 epilogue warps (lane quarter x column group) that overlap tile i's GELU with tile i+1's MMAs.
 // Tiles are walked n-fastest, so the CTAs running at the same time share x row blocks through L2.
+//
+// CL = 2: thread-block clusters of two CTAs work on two row blocks of the same n-tile in lockstep and share the weight
+// operand: CTA 0 loads the hidden box, CTA 1 the gate box, each multicast into both CTAs' stage, so a CTA pulls 32 KB
+// instead of 48 KB per k-block through the L2 -> SM path (what bounds the single-CTA kernel at K = 320: 240 KB per
+// 128 x 256 x 320 tile, 10 TB/s over the chip).  A stage is free when both CTAs' MMAs have consumed it (the MMA
+// warps commit to both CTAs' empty barriers).
 #pragma once
 #include <cuda.h>
 #include "ptx_sm100.cuh"
@@ -32,35 +38,43 @@ struct FfGegluParams {
 };
 
 constexpr int kFfStages = 4;
-constexpr int kFfThreads = 320;                    // 8 epilogue warps, TMA warp, MMA warp
+constexpr int kFfEpiWarps = 16;                    // lane quarter x group of 32 output columns
+constexpr int kFfThreads = (kFfEpiWarps + 2) * 32; // epilogue warps, TMA warp, MMA warp
 constexpr int kFfABytes = 128 * 128;               // 128 rows x 64 bf16
 constexpr int kFfBBytes = 256 * 128;               // 256 rows x 64 bf16
 constexpr int kFfStageBytes = kFfABytes + kFfBBytes;
-constexpr int kFfSmemBytes = kFfStages * kFfStageBytes + 256 + 1024;
+constexpr int kFfBiasBytes = kFfEpiWarps * 64 * 4;  // per epilogue warp: fp32 biases of its 32 hidden + 32 gate columns
+constexpr int kFfSmemBytes = kFfStages * kFfStageBytes + 256 + kFfBiasBytes + 1024;
 
+template <int CL>
 __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __grid_constant__ FfGegluParams P) {
+  static_assert(CL == 1 || CL == 2, "cluster size");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFfStages * kFfStageBytes);
   uint64_t* bar_full = bars;                       // [stages]  TMA -> MMA
   uint64_t* bar_empty = bars + kFfStages;          // [stages]  MMA -> TMA
   uint64_t* bar_acc_full = bars + 2 * kFfStages;   // [2]       MMA -> epilogue
-  uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2]       epilogue -> MMA (8 arrivals: one per warp)
+  uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2]       epilogue -> MMA (one arrival per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  float* sm_bias = reinterpret_cast<float*>(smem + kFfStages * kFfStageBytes + 256);   // [epilogue warp][hidden 32 | gate 32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  constexpr int kTmaWarp = kFfEpiWarps, kMmaWarp = kFfEpiWarps + 1;
   const int kblocks = P.K / 64;
-  const long long tiles = (long long)P.m_tiles * P.n_tiles;
+  // work unit = CL row blocks (2 u + rank of the CTA in its cluster) of one n-tile; units are walked n-fastest
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const long long units = (long long)((P.m_tiles + CL - 1) / CL) * P.n_tiles;
+  const long long u_begin = blockIdx.x / CL, u_step = gridDim.x / CL;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFfStages; ++s) {
       mbar_init(bar_full + s, 1);
-      mbar_init(bar_empty + s, 1);
+      mbar_init(bar_empty + s, CL);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full + b, 1);
-      mbar_init(bar_acc_empty + b, 8);
+      mbar_init(bar_acc_empty + b, kFfEpiWarps);
     }
     mbar_fence_init();
   }
@@ -71,23 +85,29 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kTmaWarp) {
     if (lane == 0) {
       uint32_t g = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int nt = (int)(t % P.n_tiles);
-        const int m0 = (int)(t / P.n_tiles) * 128, n0 = nt * 128;
+      for (long long u = u_begin; u < units; u += u_step) {
+        const int nt = (int)(u % P.n_tiles);
+        const int m0 = ((int)(u / P.n_tiles) * CL + (int)rank) * 128, n0 = nt * 128;
         for (int kb = 0; kb < kblocks; ++kb, ++g) {
           const int s = g % kFfStages;
           mbar_wait(bar_empty + s, ((g / kFfStages) & 1) ^ 1);
           uint8_t* a = smem + s * kFfStageBytes;
           mbar_arrive_expect_tx(bar_full + s, kFfStageBytes);
           tma_load_2d(a, &P.tm_x, bar_full + s, kb * 64, m0, kEvictNormal);
-          tma_load_2d(a + kFfABytes, &P.tm_w, bar_full + s, kb * 64, n0, kEvictLast);
-          tma_load_2d(a + kFfABytes + kFfABytes, &P.tm_w, bar_full + s, kb * 64, P.N + n0, kEvictLast);
+          if (CL == 1) {
+            tma_load_2d(a + kFfABytes, &P.tm_w, bar_full + s, kb * 64, n0, kEvictLast);
+            tma_load_2d(a + kFfABytes + kFfABytes, &P.tm_w, bar_full + s, kb * 64, P.N + n0, kEvictLast);
+          } else {   // this CTA's half of the weight operand, delivered to both CTAs of the cluster
+            tma_load_2d_multicast(a + kFfABytes + rank * kFfABytes, &P.tm_w, bar_full + s, kb * 64,
+                                  (int)rank * P.N + n0, (uint16_t)0b11, kEvictLast);
+          }
         }
       }
     }
@@ -96,7 +116,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
     const uint64_t desc0 = make_smem_desc_sw128(0, 16, 1024);
     uint32_t g = 0;
     int i = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+    for (long long u = u_begin; u < units; u += u_step, ++i) {
       const int b = i & 1;
       mbar_wait(bar_acc_empty + b, ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
       tc_fence_after();
@@ -113,53 +133,57 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
             const uint64_t db = desc0 | (uint64_t)((ba + kk * 2) & 0x3FFF);
             umma_ss(tmem_base + b * 256, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
           }
-          tc_commit(bar_empty + s);
+          if (CL == 1) tc_commit(bar_empty + s);
+          else tc_commit_multicast(bar_empty + s, (uint16_t)0b11);
           if (kb == kblocks - 1) tc_commit(bar_acc_full + b);
         }
         __syncwarp();
       }
     }
   } else {
-    // =========================== epilogue: warp = (lane quarter, column half) ===========================
+    // =========================== epilogue: warp = (lane quarter, column group) ===========================
+    constexpr int CG = kFfEpiWarps / 4, CW = 128 / CG, NCH = CW / 16;   // column groups, their width, 16-column chunks
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     int i = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+    for (long long u = u_begin; u < units; u += u_step, ++i) {
       const int b = i & 1;
-      const int nt = (int)(t % P.n_tiles);
-      const long long row = (t / P.n_tiles) * 128 + quarter * 32 + lane;
-      const int n0 = nt * 128 + half * 64;
+      const int nt = (int)(u % P.n_tiles);
+      const long long row = ((u / P.n_tiles) * CL + rank) * 128 + quarter * 32 + lane;
+      const int n0 = nt * 128 + half * CW;
       mbar_wait(bar_acc_full + b, (i >> 1) & 1);
       tc_fence_after();
-      const uint32_t tm = tmem_base + lane_addr + b * 256 + half * 64;
+      const uint32_t tm = tmem_base + lane_addr + b * 256 + half * CW;
       __nv_bfloat16* orow = P.out + row * P.ld + n0;
+      // this warp's biases as fp32 pairs in its own shared-memory slot (no cross-warp synchronisation)
+      float* wb = sm_bias + warp * 64;
+      __syncwarp();   // the previous tile's reads of the slot are done
+      wb[lane] = P.bias ? __bfloat162float(P.bias[n0 + lane]) : 0.f;
+      wb[32 + lane] = P.bias ? __bfloat162float(P.bias[P.N + n0 + lane]) : 0.f;
+      __syncwarp();
       // chunks of 16 columns, software-pipelined: the TMEM loads of chunk ch + 1 are in flight under the GELUs of ch
       uint32_t h[2][16], gt[2][16];
       tmem_ld_x16(tm, h[0]);
       tmem_ld_x16(tm + 128, gt[0]);
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t bh[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, bg[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        if (P.bias) {
-          const uint4* ph = reinterpret_cast<const uint4*>(P.bias + n0 + ch * 16);
-          const uint4* pg = reinterpret_cast<const uint4*>(P.bias + P.N + n0 + ch * 16);
-          const uint4 h0 = __ldg(ph), h1 = __ldg(ph + 1), g0 = __ldg(pg), g1 = __ldg(pg + 1);
-          bh[0] = h0.x; bh[1] = h0.y; bh[2] = h0.z; bh[3] = h0.w; bh[4] = h1.x; bh[5] = h1.y; bh[6] = h1.z; bh[7] = h1.w;
-          bg[0] = g0.x; bg[1] = g0.y; bg[2] = g0.z; bg[3] = g0.w; bg[4] = g1.x; bg[5] = g1.y; bg[6] = g1.z; bg[7] = g1.w;
-        }
+      for (int ch = 0; ch < NCH; ++ch) {
         tc_wait_ld();
-        if (ch + 1 < 4) {
+        if (ch + 1 < NCH) {
           tmem_ld_x16(tm + (ch + 1) * 16, h[(ch + 1) & 1]);
           tmem_ld_x16(tm + 128 + (ch + 1) * 16, gt[(ch + 1) & 1]);
         }
         const uint32_t* hc = h[ch & 1];
         const uint32_t* gc = gt[ch & 1];
+        const uint64_t* bh2 = reinterpret_cast<const uint64_t*>(wb + ch * 16);
+        const uint64_t* bg2 = reinterpret_cast<const uint64_t*>(wb + 32 + ch * 16);
         uint32_t o[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float h0 = __uint_as_float(hc[2 * k]) + bf16_lo(bh[k]), h1 = __uint_as_float(hc[2 * k + 1]) + bf16_hi(bh[k]);
-          const float g0 = __uint_as_float(gc[2 * k]) + bf16_lo(bg[k]), g1 = __uint_as_float(gc[2 * k + 1]) + bf16_hi(bg[k]);
-          o[k] = bf16_pack(h0 * gelu_erf_fast(g0), h1 * gelu_erf_fast(g1));
+          const uint64_t h2 = f2_add(f2_pack(__uint_as_float(hc[2 * k]), __uint_as_float(hc[2 * k + 1])), bh2[k]);
+          const uint64_t g2 = f2_add(f2_pack(__uint_as_float(gc[2 * k]), __uint_as_float(gc[2 * k + 1])), bg2[k]);
+          float r0, r1;
+          f2_unpack(geglu_pair(h2, g2), r0, r1);
+          o[k] = bf16_pack(r0, r1);
         }
         if (row < P.rows) {
           uint4* dst = reinterpret_cast<uint4*>(orow + ch * 16);
@@ -177,6 +201,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "ptx_sm100.cuh"   // packed fp32x2 helpers
 
 namespace i2v {
 
@@ -126,6 +127,94 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict_
   }
 }
 
+// The SD1.5 widths (C = 320 / 640 / 1280 = 40 * LPR channels-of-8) as sub-warp rows: LPR = 8 / 16 / 32 lanes share a row,
+// five 16-byte vectors per lane (every lane busy, where the warp-per-row kernel above idles 3 of 8 load slots at
+// C = 320), 32 / LPR rows per warp at once, persistent warps, reductions are LPR-wide shuffles.  Same arithmetic and
+// rounding points as layernorm_kernel.
+template <int LPR>
+__global__ void __launch_bounds__(256, 4) layernorm5_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                         const uint4* __restrict__ w, const uint4* __restrict__ b,
+                                                         const uint4* __restrict__ pe, int pe_rows, long long rows,
+                                                         float eps, const uint4* __restrict__ pre) {
+  constexpr int NV = 5, RPW = 32 / LPR, U = 1, nvec = NV * LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rw = lane / LPR;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  constexpr float inv_n = 1.f / (float)(nvec * 8);
+  for (long long base = warp * (RPW * U); base < rows; base += nwarps * (RPW * U)) {
+    uint4 v[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * RPW + rw;
+      const uint4* xr = x + row * nvec + sub;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[u][i] = row < rows ? xr[LPR * i] : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = base + u * RPW + rw;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        uint32_t ww[4] = {v[u][i].x, v[u][i].y, v[u][i].z, v[u][i].w};
+        if (pre) {   // x + pre[c], rounded to bf16 as the producer's own bias add would have been
+          const uint4 pq = pre[sub + LPR * i];   // L1-resident
+          const uint32_t pp[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ww[k] = bf16_pack(bf16_lo(ww[k]) + bf16_lo(pp[k]), bf16_hi(ww[k]) + bf16_hi(pp[k]));
+          v[u][i] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s += bf16_lo(ww[k]) + bf16_hi(ww[k]);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_n;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t ww[4] = {v[u][i].x, v[u][i].y, v[u][i].z, v[u][i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = bf16_lo(ww[k]) - mean, bb = bf16_hi(ww[k]) - mean;
+          q = fmaf(a, a, fmaf(bb, bb, q));
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * inv_n + eps);
+      if (row >= rows) continue;   // (after the shuffles: every lane of the warp takes part in them)
+      uint4* yr = y + row * nvec + sub;
+      const uint4* per = pe ? pe + (row % pe_rows) * nvec + sub : nullptr;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t xin[4] = {v[u][i].x, v[u][i].y, v[u][i].z, v[u][i].w};
+        const uint4 wq = w[sub + LPR * i], bq = b[sub + LPR * i];   // L1-resident
+        const uint32_t win[4] = {wq.x, wq.y, wq.z, wq.w};
+        const uint32_t bin[4] = {bq.x, bq.y, bq.z, bq.w};
+        uint32_t pin[4] = {0u, 0u, 0u, 0u};
+        if (per) {
+          const uint4 t = per[LPR * i];
+          pin[0] = t.x; pin[1] = t.y; pin[2] = t.z; pin[3] = t.w;
+        }
+        uint32_t out[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float lo = (bf16_lo(xin[k]) - mean) * rstd * bf16_lo(win[k]) + bf16_lo(bin[k]);
+          float hi = (bf16_hi(xin[k]) - mean) * rstd * bf16_hi(win[k]) + bf16_hi(bin[k]);
+          if (per) {
+            const uint32_t rr = bf16_pack(lo, hi);
+            lo = bf16_lo(rr) + bf16_lo(pin[k]);
+            hi = bf16_hi(rr) + bf16_hi(pin[k]);
+          }
+          out[k] = bf16_pack(lo, hi);
+        }
+        yr[LPR * i] = make_uint4(out[0], out[1], out[2], out[3]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // GEGLU: y[r, c] = x[r, c] * gelu(x[r, D + c]), exact (erf) GELU.  x is [rows, 2D], y is [rows, D].
 // ---------------------------------------------------------------------------------------------------------------
@@ -158,6 +247,27 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
   q = fmaf(q, t, -0.142248368f);
   q = fmaf(q, t, 0.127414796f);
   return fmaf(-(ag * e), q * t, fmaxf(g, 0.f));
+}
+
+// Two of them at once on packed fp32 pairs (FFMA2 / FMUL2 take one issue slot for both lanes): h * gelu(g) for a pair.
+__device__ __forceinline__ uint64_t geglu_pair(uint64_t h2, uint64_t g2) {
+  float g0, g1;
+  f2_unpack(g2, g0, g1);
+  const float a0 = fabsf(g0), a1 = fabsf(g1);
+  const uint64_t ag2 = f2_pack(a0, a1);
+  float d0, d1, x0, x1;
+  f2_unpack(f2_fma(ag2, f2_pack(0.23164189f, 0.23164189f), f2_pack(1.f, 1.f)), d0, d1);
+  f2_unpack(f2_mul(f2_mul(g2, g2), f2_pack(-0.72134752f, -0.72134752f)), x0, x1);
+  const uint64_t t2 = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  const uint64_t e2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+  uint64_t q = f2_fma(t2, f2_pack(0.5307027145f, 0.5307027145f), f2_pack(-0.7265760135f, -0.7265760135f));
+  q = f2_fma(q, t2, f2_pack(0.7107068705f, 0.7107068705f));
+  q = f2_fma(q, t2, f2_pack(-0.142248368f, -0.142248368f));
+  q = f2_fma(q, t2, f2_pack(0.127414796f, 0.127414796f));
+  const uint64_t relu2 = f2_pack(fmaxf(g0, 0.f), fmaxf(g1, 0.f));
+  // gelu = relu(g) - (|g| e) (q t)
+  const uint64_t neg = f2_mul(f2_mul(ag2, e2), f2_mul(q, t2));
+  return f2_mul(h2, f2_sub(relu2, neg));
 }
 
 __device__ __forceinline__ uint4 geglu_vec(const uint4 h, const uint4 g) {
@@ -395,15 +505,22 @@ __global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const GnNhwcParams P
   const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
   if (trow < rpp) {
     const uint4* base = reinterpret_cast<const uint4*>(P.x + (long long)n * P.S * P.C) + tcol;
-    for (int r = r0 + trow; r < r1; r += rpp) {
-      const uint4 v = base[(long long)r * VC];
-      const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+    for (int r = r0 + trow; r < r1; r += 4 * rpp) {   // four row vectors in flight per thread
+      uint4 v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float a = bf16_lo(ww[k]), b = bf16_hi(ww[k]);
-        if (has_add) { a = bf16_round(a + ad[2 * k]); b = bf16_round(b + ad[2 * k + 1]); }
-        s[2 * k] += a; q[2 * k] += a * a;
-        s[2 * k + 1] += b; q[2 * k + 1] += b * b;
+      for (int u = 0; u < 4; ++u)
+        if (r + u * rpp < r1) v[u] = base[(long long)(r + u * rpp) * VC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * rpp >= r1) break;
+        const uint32_t ww[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a = bf16_lo(ww[k]), b = bf16_hi(ww[k]);
+          if (has_add) { a = bf16_round(a + ad[2 * k]); b = bf16_round(b + ad[2 * k + 1]); }
+          s[2 * k] += a; q[2 * k] = fmaf(a, a, q[2 * k]);
+          s[2 * k + 1] += b; q[2 * k + 1] = fmaf(b, b, q[2 * k + 1]);
+        }
       }
     }
 #pragma unroll
@@ -449,55 +566,63 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnNhwcParams P) 
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_rows_kernel(const GnNhwcParams P) {
-  extern __shared__ float sm_tab[];   // A[C], B[C], T[C]:  y = (x + T) * A + B
+// Thread = (channel vector, row phase): the thread's eight channels keep their (A, B, T) coefficients in registers
+// (y = (x + T) * A + B), so the row loop is loads, eight FMAs and a store per 16-byte vector; block = C/8 * rows-per-pass.
+__global__ void __launch_bounds__(512) gn_apply_rows_kernel(const GnNhwcParams P) {
   const int chunk = blockIdx.x, n = blockIdx.y;
   const int v = n / P.fg, f = n - v * P.fg;
-  const int cg = P.C / P.G;
-  for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
-    const float mean = P.stats[2 * (v * P.G + c / cg)], rstd = P.stats[2 * (v * P.G + c / cg) + 1];
-    const float a = rstd * __bfloat162float(P.w[c]);
-    sm_tab[c] = a;
-    sm_tab[P.C + c] = __bfloat162float(P.b[c]) - mean * a;
-    sm_tab[2 * P.C + c] = P.add ? __bfloat162float(P.add[(long long)n * P.C + c]) : 0.f;
-  }
-  __syncthreads();
   const int VC = P.C / 8;
-  const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
+  const int rpp = blockDim.x / VC;
+  const int tcol = threadIdx.x % VC, trow = threadIdx.x / VC;
+  if (trow >= rpp) return;
+  const int cg = P.C / P.G;
   const bool has_add = P.add != nullptr;
-  // flat index space (row, 16-byte vector) of the chunk, every thread keeps four vectors in flight
-  const int total = (r1 - r0) * VC;
-  const uint4* src = reinterpret_cast<const uint4*>(P.x + ((long long)n * P.S + r0) * P.C);
-  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+  float A[8], B[8], T[8];
+  {
+    const uint4 wv = *reinterpret_cast<const uint4*>(P.w + tcol * 8);
+    const uint4 bv = *reinterpret_cast<const uint4*>(P.b + tcol * 8);
+    uint4 av = make_uint4(0u, 0u, 0u, 0u);
+    if (has_add) av = *reinterpret_cast<const uint4*>(P.add + (long long)n * P.C + tcol * 8);
+    const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w}, a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = (tcol * 8 + k) / cg;
+      const float mean = P.stats[2 * (v * P.G + g)], rstd = P.stats[2 * (v * P.G + g) + 1];
+      const float wk = (k & 1) ? bf16_hi(w4[k >> 1]) : bf16_lo(w4[k >> 1]);
+      const float bk = (k & 1) ? bf16_hi(b4[k >> 1]) : bf16_lo(b4[k >> 1]);
+      A[k] = rstd * wk;
+      B[k] = bk - mean * A[k];
+      T[k] = (k & 1) ? bf16_hi(a4[k >> 1]) : bf16_lo(a4[k >> 1]);
+    }
+  }
+  const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
+  const uint4* src = reinterpret_cast<const uint4*>(P.x + (long long)n * P.S * P.C) + tcol;
+  for (int r = r0 + trow; r < r1; r += 4 * rpp) {   // four row vectors in flight per thread
     uint4 xv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * blockDim.x;
-      if (e < total) xv[u] = src[e];
-    }
+    for (int u = 0; u < 4; ++u)
+      if (r + u * rpp < r1) xv[u] = src[(long long)(r + u * rpp) * VC];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * blockDim.x;
-      if (e >= total) break;
-      const int r = r0 + e / VC, cv = e % VC;
-      const long long orow = P.perm ? (((long long)v * P.S + r) * P.fg + f) : ((long long)n * P.S + r);
+      const int rr = r + u * rpp;
+      if (rr >= r1) break;
+      const long long orow = P.perm ? (((long long)v * P.S + rr) * P.fg + f) : ((long long)n * P.S + rr);
       const uint32_t ww[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int c = cv * 8 + 2 * k;
         float a = bf16_lo(ww[k]), b = bf16_hi(ww[k]);
-        if (has_add) { a = bf16_round(a + sm_tab[2 * P.C + c]); b = bf16_round(b + sm_tab[2 * P.C + c + 1]); }
-        a = fmaf(a, sm_tab[c], sm_tab[P.C + c]);
-        b = fmaf(b, sm_tab[c + 1], sm_tab[P.C + c + 1]);
-        if (P.silu) {
+        if (has_add) { a = bf16_round(a + T[2 * k]); b = bf16_round(b + T[2 * k + 1]); }
+        a = fmaf(a, A[2 * k], B[2 * k]);
+        b = fmaf(b, A[2 * k + 1], B[2 * k + 1]);
+        if (P.silu) {   // x * sigmoid(x) on the bf16-rounded GroupNorm output, as the reference's two ops
           a = bf16_round(a); b = bf16_round(b);
-          a = a / (1.f + __expf(-a));
-          b = b / (1.f + __expf(-b));
+          a *= rcp_approx(1.f + ex2_approx(-1.4426950408889634f * a));
+          b *= rcp_approx(1.f + ex2_approx(-1.4426950408889634f * b));
         }
         o[k] = bf16_pack(a, b);
       }
-      reinterpret_cast<uint4*>(P.out + orow * P.C)[cv] = make_uint4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<uint4*>(P.out + orow * P.C)[tcol] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
