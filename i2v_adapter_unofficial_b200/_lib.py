@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "i2v_layernorm_pre_fwd",
     "i2v_geglu_ld_fwd",
     "i2v_ff_geglu_fwd",
+    "i2v_upsample2x_nhwc",
     "i2v_geglu_fwd",
     "i2v_gn_stats",
     "i2v_gn_apply_transpose",
@@ -105,6 +106,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_layernorm_pre_fwd.argtypes = [p, p, p, p, p, p, ll, i, i, f, p]
     lib.i2v_geglu_ld_fwd.restype = i
     lib.i2v_geglu_ld_fwd.argtypes = [p, p, ll, i, i, p]
+    lib.i2v_upsample2x_nhwc.restype = i
+    lib.i2v_upsample2x_nhwc.argtypes = [p, p, i, i, i, i, p]
     lib.i2v_ff_geglu_fwd.restype = i
     lib.i2v_ff_geglu_fwd.argtypes = [p, p, p, p, ll, i, i, i, p]
     lib.i2v_gn_stats.restype = i

@@ -965,8 +965,9 @@ int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, voi
                            void* stream) {
   if (N <= 0 || S <= 0 || C <= 0 || fg <= 0 || C % 8 || N % fg)
     return fail(I2V_ERR_BAD_SHAPE, "rows_residual: bad shape N=%d S=%d C=%d fg=%d", N, S, C, fg);
-  if (!y || !res || !out) return fail(I2V_ERR_BAD_SHAPE, "rows_residual: null pointer");
-  if (!aligned16(y) || !aligned16(res) || !aligned16(out) || (bias && !aligned16(bias)))
+  if (!y || !out || (!res && !bias)) return fail(I2V_ERR_BAD_SHAPE, "rows_residual: null pointer");
+  if (!res && fg != 1) return fail(I2V_ERR_BAD_SHAPE, "rows_residual: the bias-only form takes fg = 1");
+  if (!aligned16(y) || (res && !aligned16(res)) || !aligned16(out) || (bias && !aligned16(bias)))
     return fail(I2V_ERR_MISALIGNED, "rows_residual: pointers must be 16-byte aligned");
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
@@ -979,6 +980,22 @@ int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, voi
   long long blocks = (rows + 7) / 8;
   if (blocks > 8LL * di->sms) blocks = 8LL * di->sms;
   i2v::rows_residual_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int i2v_upsample2x_nhwc(const void* x, void* out, int N, int h, int w, int C, void* stream) {
+  if (N <= 0 || h <= 0 || w <= 0 || C <= 0 || C % 8) return fail(I2V_ERR_BAD_SHAPE, "upsample2x: bad shape N=%d h=%d w=%d C=%d", N, h, w, C);
+  if (!x || !out) return fail(I2V_ERR_BAD_SHAPE, "upsample2x: null pointer");
+  if (!aligned16(x) || !aligned16(out)) return fail(I2V_ERR_MISALIGNED, "upsample2x: pointers must be 16-byte aligned");
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  const long long total = (long long)N * h * w * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16LL * di->sms) blocks = 16LL * di->sms;
+  i2v::upsample2x_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, N, h, w, C / 8);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

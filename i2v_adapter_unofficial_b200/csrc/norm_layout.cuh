@@ -644,10 +644,10 @@ __global__ void __launch_bounds__(256) rows_residual_kernel(const RowsResidualPa
     const int n = (int)(row / P.S), s = (int)(row - (long long)n * P.S);
     const int v = n / P.fg, f = n - v * P.fg;
     const uint4* ysrc = reinterpret_cast<const uint4*>(P.y + (((long long)v * P.S + s) * P.fg + f) * P.C);
-    const uint4* rsrc = reinterpret_cast<const uint4*>(P.res + row * P.C);
+    const uint4* rsrc = P.res ? reinterpret_cast<const uint4*>(P.res + row * P.C) : nullptr;   // null: out = y + bias
     uint4* dst = reinterpret_cast<uint4*>(P.out + row * P.C);
     for (int cv = lane; cv < VC; cv += 32) {
-      const uint4 a = ysrc[cv], b = rsrc[cv];
+      const uint4 a = ysrc[cv], b = rsrc ? rsrc[cv] : make_uint4(0u, 0u, 0u, 0u);
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
       uint32_t cw[4] = {0u, 0u, 0u, 0u};
       if (P.bias) {
@@ -662,10 +662,33 @@ __global__ void __launch_bounds__(256) rows_residual_kernel(const RowsResidualPa
           const uint32_t r = bf16_pack(lo + bf16_lo(cw[k]), hi + bf16_hi(cw[k]));
           lo = bf16_lo(r); hi = bf16_hi(r);
         }
-        o[k] = bf16_pack(lo + bf16_lo(bw[k]), hi + bf16_hi(bw[k]));
+        o[k] = rsrc ? bf16_pack(lo + bf16_lo(bw[k]), hi + bf16_hi(bw[k])) : bf16_pack(lo, hi);
       }
       dst[cv] = make_uint4(o[0], o[1], o[2], o[3]);
     }
+  }
+}
+
+// Nearest-neighbour 2x upsampling of a channels-last activation: out[n, 2y + dy, 2x + dx, :] = in[n, y, x, :]
+// (Upsample2D's F.interpolate(scale_factor=2, mode="nearest") ahead of its convolution).  One 16-byte vector per
+// thread-iteration: read once, written to the four output positions; consecutive threads take consecutive vectors of
+// a row, so every access is a full line.  ATen's NHWC kernel runs this at 0.4 TB/s.
+__global__ void __launch_bounds__(256) upsample2x_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ out,
+                                                              int N, int h, int w, int VC /* C / 8 */) {
+  const long long total = (long long)N * h * w * VC;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int cv = (int)(e % VC);
+    long long p = e / VC;
+    const int xx = (int)(p % w);  p /= w;
+    const int yy = (int)(p % h);
+    const long long n = p / h;
+    const uint4 v = x[e];
+    uint4* o = out + (((n * 2 * h + 2 * yy) * 2 * w) + 2 * xx) * VC + cv;
+    o[0] = v;
+    o[VC] = v;
+    o[(long long)2 * w * VC] = v;
+    o[(long long)2 * w * VC + VC] = v;
   }
 }
 

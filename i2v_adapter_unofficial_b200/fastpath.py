@@ -389,14 +389,59 @@ def _make_resnet_forward(module: nn.Module, original: Callable):
             h = h.contiguous(memory_format=torch.channels_last)
         h = ops.group_norm_nhwc(h, n2.weight, n2.bias, n2.num_groups, n2.eps, 1, silu=True, add=t)
         h = F.conv2d(h, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
-        if getattr(module, "conv_shortcut", None) is not None:
-            x = module.conv_shortcut(x)
+        cs = getattr(module, "conv_shortcut", None)
+        bias = c2.bias
+        if cs is not None:
+            if isinstance(cs, nn.Conv2d) and cs.padding_mode == "zeros" and ops.is_channels_last(h):
+                # the shortcut convolution's bias rides in the same residual pass as conv2's
+                x = F.conv2d(x, cs.weight, None, cs.stride, cs.padding, cs.dilation, cs.groups)
+                if cs.bias is not None:
+                    bias = cs.bias if bias is None else bias + cs.bias
+            else:
+                x = cs(x)
         if ops.is_channels_last(x) and ops.is_channels_last(h):
-            out = ops.nhwc_add(x, h, c2.bias)          # x + h + bias[c] in one pass
+            out = ops.nhwc_add(x, h, bias)             # x + h + bias[c] in one pass
         else:
             out = x + (h if c2.bias is None else h + c2.bias[None, :, None, None])
         osf = getattr(module, "output_scale_factor", 1.0)
         return out if osf == 1.0 else out / osf
+
+    return forward
+
+
+def _conv_bias_nhwc(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """``conv(x)`` with the bias applied by one full-bandwidth in-place pass (channels-last bf16)."""
+    y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if conv.bias is None:
+        return y
+    if ops.is_channels_last(y) and y.shape[1] % 8 == 0:
+        return ops.nhwc_bias_add_(y, conv.bias)
+    return y + conv.bias[None, :, None, None]
+
+
+def _sampler_ok(module: nn.Module, x: torch.Tensor) -> bool:
+    conv = getattr(module, "conv", None)
+    return (_fast_ok(x, module) and isinstance(conv, nn.Conv2d) and conv.padding_mode == "zeros" and x.dim() == 4
+            and ops.is_channels_last(x) and x.shape[1] % 8 == 0)
+
+
+def _make_upsample_forward(module: nn.Module, original: Callable):
+    """Upsample2D: nearest 2x interpolation as one read / four writes per vector, then the convolution."""
+    @functools.wraps(original)
+    def forward(x, output_size=None, *args, **kwargs):
+        if output_size is not None or not _sampler_ok(module, x):
+            return original(x, output_size, *args, **kwargs)
+        return _conv_bias_nhwc(module.conv, ops.upsample2x_nhwc(x))
+
+    return forward
+
+
+def _make_downsample_forward(module: nn.Module, original: Callable):
+    @functools.wraps(original)
+    def forward(x, *args, **kwargs):
+        if not _sampler_ok(module, x):
+            return original(x, *args, **kwargs)
+        return _conv_bias_nhwc(module.conv, x)
 
     return forward
 
@@ -443,4 +488,8 @@ def install_fast_forwards(root: nn.Module) -> List[Callable[[], None]]:
             patch(module, _make_temporal_forward(module, module.forward))
         elif name == "ResnetBlock2D":
             patch(module, _make_resnet_forward(module, module.forward))
+        elif name == "Upsample2D":
+            patch(module, _make_upsample_forward(module, module.forward))
+        elif name == "Downsample2D":
+            patch(module, _make_downsample_forward(module, module.forward))
     return undo

@@ -394,6 +394,32 @@ def nhwc_add(x: torch.Tensor, y: torch.Tensor, bias: Optional[torch.Tensor] = No
     return out
 
 
+def nhwc_bias_add_(x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """In place x += bias[c] on a channels-last (N, C, h, w) tensor: a convolution bias as one full-bandwidth pass
+    (cuDNN's bf16 channels-last convolutions apply it with a separate strided elementwise kernel)."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and is_channels_last(x) and x.shape[1] % 8 == 0):
+        raise RuntimeError("nhwc_bias_add_: needs a CUDA bf16 channels-last tensor with C % 8 == 0 (no CPU fallback)")
+    N, C, h, w = x.shape
+    bias = bias.to(dtype=x.dtype).contiguous()
+    lib = _lib.load()
+    with _on_device(x.device):
+        _lib.check(lib.i2v_rows_residual_bias(x.data_ptr(), None, bias.data_ptr(), x.data_ptr(), N, h * w, C, 1,
+                                              _stream(x.device)))
+    return x
+
+
+def upsample2x_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """``F.interpolate(x, scale_factor=2.0, mode="nearest")`` for a channels-last bf16 (N, C, h, w) tensor."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and is_channels_last(x) and x.shape[1] % 8 == 0):
+        raise RuntimeError("upsample2x_nhwc: needs a CUDA bf16 channels-last tensor with C % 8 == 0 (no CPU fallback)")
+    N, C, h, w = x.shape
+    out = torch.empty((N, C, 2 * h, 2 * w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    lib = _lib.load()
+    with _on_device(x.device):
+        _lib.check(lib.i2v_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), N, h, w, C, _stream(x.device)))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 # torch.library registration: torch.ops.i2v_b200.*  (CUDA key only -> CPU tensors raise NotImplementedError)
 # ----------------------------------------------------------------------------------------------------------

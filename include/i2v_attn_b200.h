@@ -185,6 +185,10 @@ int i2v_rows_residual(const void* y, const void* res, void* out, int N, int S, i
  * conv2's bias folded in (cuDNN would spend a separate broadcast-add pass on it). */
 int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, void* out, int N, int S, int C, int fg,
                            void* stream);
+/* i2v_upsample2x_nhwc: nearest-neighbour 2x upsampling of a channels-last [N, h, w, C] activation into [N, 2h, 2w, C]
+ *   (Upsample2D's interpolate ahead of its convolution; C % 8 == 0).  With res == NULL, i2v_rows_residual_bias is the
+ *   in-place-capable per-channel bias add out = y + bias (a convolution bias cuDNN would apply as a separate pass). */
+int i2v_upsample2x_nhwc(const void* x, void* out, int N, int h, int w, int C, void* stream);
 
 /* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
  * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),

@@ -359,3 +359,36 @@ def test_ff_geglu_rejects_unsupported_shapes():
     x, w = _rand((64, 64), 46).to(DEV), _rand((192, 64), 47).to(DEV)
     with pytest.raises(RuntimeError, match="N % 128"):
         ops.ff_geglu(x, w)
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 5, 7), (2, 1280, 8, 8), (32, 640, 16, 16)])
+def test_upsample2x_nhwc_is_exact(shape):
+    x = _rand(shape, 51).to(DEV).contiguous(memory_format=torch.channels_last)
+    y = ops.upsample2x_nhwc(x)
+    ref = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    assert ops.is_channels_last(y) and y.shape == ref.shape
+    assert torch.equal(y, ref)
+
+
+def test_nhwc_bias_add_in_place():
+    x = _rand((3, 320, 6, 5), 52, 2.0).to(DEV).contiguous(memory_format=torch.channels_last)
+    b = _rand((320,), 53).to(DEV)
+    ref = (x.float() + b.float()[None, :, None, None]).to(torch.bfloat16)
+    out = ops.nhwc_bias_add_(x, b)
+    assert out.data_ptr() == x.data_ptr() and torch.equal(out, ref)
+
+
+def test_sampler_fast_paths_match_the_modules():
+    from i2v_adapter_unofficial_b200.hostmodel.layers import Downsample2D, Upsample2D
+
+    torch.manual_seed(5)
+    for cls, shape in ((Upsample2D, (4, 64, 8, 8)), (Downsample2D, (4, 64, 16, 16))):
+        m = cls(64).eval().to(DEV, torch.bfloat16).to(memory_format=torch.channels_last)
+        x = _rand(shape, 54).to(DEV).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            ref = m(x).float()
+            handle = install(m)
+            out = m(x).float()
+            handle.uninstall()
+        assert out.shape == ref.shape
+        assert (out - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
