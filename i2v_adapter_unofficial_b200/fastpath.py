@@ -446,6 +446,29 @@ def _make_downsample_forward(module: nn.Module, original: Callable):
     return forward
 
 
+def _make_out_norm_forwards(norm: nn.GroupNorm, act: nn.Module, norm_forward: Callable, act_forward: Callable):
+    """The UNet's tail ``conv_act(conv_norm_out(sample))`` (reference unet_motion_cross_frame_attn.py:1437-1439) as one
+    GroupNorm + SiLU pass of the channels-last kernels; the activation module becomes the identity for that call."""
+    state = {"fused": False}
+
+    @functools.wraps(norm_forward)
+    def norm_fwd(x):
+        if _fast_ok(x, norm) and norm.affine and x.dim() == 4 and _nhwc_ok(x, norm):
+            state["fused"] = True
+            return ops.group_norm_nhwc(x, norm.weight, norm.bias, norm.num_groups, norm.eps, 1, silu=True)
+        state["fused"] = False
+        return norm_forward(x)
+
+    @functools.wraps(act_forward)
+    def act_fwd(x):
+        if state["fused"]:
+            state["fused"] = False
+            return x
+        return act_forward(x)
+
+    return norm_fwd, act_fwd
+
+
 class _Sample:
     """``.sample`` attribute and tuple-style ``[0]`` (what the call sites use, e.g. unet_motion_cross_frame_attn.py:326)."""
 
@@ -475,6 +498,12 @@ def install_fast_forwards(root: nn.Module) -> List[Callable[[], None]]:
                 m.__dict__.pop("forward", None)
 
         undo.append(restore)
+
+    out_norm, out_act = getattr(root, "conv_norm_out", None), getattr(root, "conv_act", None)
+    if isinstance(out_norm, nn.GroupNorm) and _is_silu(out_act) and isinstance(out_act, nn.Module):
+        norm_fwd, act_fwd = _make_out_norm_forwards(out_norm, out_act, out_norm.forward, out_act.forward)
+        patch(out_norm, norm_fwd)
+        patch(out_act, act_fwd)
 
     for module in list(root.modules()):
         name = type(module).__name__
