@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = (
     "i2v_untranspose_residual",
     "i2v_gn_nhwc_scratch_floats",
     "i2v_gn_nhwc",
+    "i2v_gn_nhwc_cat",
     "i2v_rows_residual",
     "i2v_rows_residual_bias",
 )
@@ -120,6 +121,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_gn_nhwc_scratch_floats.argtypes = [i, i]
     lib.i2v_gn_nhwc.restype = i
     lib.i2v_gn_nhwc.argtypes = [p, p, p, p, p, p, i, i, i, i, i, f, i, i, p]
+    lib.i2v_gn_nhwc_cat.restype = i
+    lib.i2v_gn_nhwc_cat.argtypes = [p, p, i, p, p, p, p, p, i, i, i, i, i, f, i, i, p]
     lib.i2v_rows_residual.restype = i
     lib.i2v_rows_residual.argtypes = [p, p, p, i, i, i, i, p]
     lib.i2v_rows_residual_bias.restype = i

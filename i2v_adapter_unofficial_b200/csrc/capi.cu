@@ -922,6 +922,13 @@ long long i2v_gn_nhwc_scratch_floats(int N, int G) { return (long long)N * G * 2
 
 int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, void* out, float* scratch, int N, int S,
                 int C, int G, int fg, float eps, int silu, int perm, void* stream) {
+  return i2v_gn_nhwc_cat(x, nullptr, C, add, w, b, out, scratch, N, S, C, G, fg, eps, silu, perm, stream);
+}
+
+int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, const void* w, const void* b, void* out,
+                    float* scratch, int N, int S, int C, int G, int fg, float eps, int silu, int perm, void* stream) {
+  if (x2 && (C1 <= 0 || C1 >= C || C1 % 8 || !aligned16(x2)))
+    return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc_cat: the first source needs 0 < C1 < C, C1 %% 8 == 0 and a 16-byte aligned second source (C1=%d C=%d)", C1, C);
   if (N <= 0 || S <= 0 || C <= 0 || G <= 0 || fg <= 0 || C % G || C % 8 || N % fg)
     return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc: bad shape N=%d S=%d C=%d G=%d fg=%d", N, S, C, G, fg);
   if (C / 8 > 512 || G > 256) return fail(I2V_ERR_UNSUPPORTED, "gn_nhwc: C <= 4096 and G <= 256 only (C=%d G=%d)", C, G);
@@ -934,6 +941,7 @@ int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, vo
   if (rc) return rc;
   i2v::GnNhwcParams P;
   P.x = (const __nv_bfloat16*)x; P.out = (__nv_bfloat16*)out; P.add = (const __nv_bfloat16*)add;
+  P.x2 = (const __nv_bfloat16*)x2; P.C1 = x2 ? C1 : C;
   P.w = (const __nv_bfloat16*)w; P.b = (const __nv_bfloat16*)b;
   P.N = N; P.S = S; P.C = C; P.G = G; P.fg = fg; P.eps = eps; P.silu = silu; P.perm = perm;
   int ch = (4 * di->sms + N - 1) / N;   // ~4 CTAs per SM in total

@@ -467,7 +467,9 @@ __global__ void __launch_bounds__(256) untranspose_residual_kernel(const Untrans
 // bf16 each (three PyTorch ops); the kernels round at the same places.
 // ===============================================================================================================
 struct GnNhwcParams {
-  const __nv_bfloat16* x;      // [N, S, C]
+  const __nv_bfloat16* x;      // [N, S, C]   (two-source form: [N, S, C1], channels [0, C1) of the virtual concatenation)
+  const __nv_bfloat16* x2;     // null, or [N, S, C - C1]: channels [C1, C) -- the up blocks' torch.cat([hidden, skip], 1)
+  int C1;                      //   (:457 of unet_motion_cross_frame_attn.py) is never materialised
   __nv_bfloat16* out;          // [N, S, C] (perm = 0) or [V, S, fg, C] (perm = 1)
   const __nv_bfloat16* add;    // [N, C] or null
   float* partial;              // [N, CH, G, 2]
@@ -504,12 +506,16 @@ __global__ void __launch_bounds__(512) gn_stats_nhwc_kernel(const GnNhwcParams P
   }
   const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
   if (trow < rpp) {
-    const uint4* base = reinterpret_cast<const uint4*>(P.x + (long long)n * P.S * P.C) + tcol;
+    // this thread's channel vector lives in the first or in the second source (row pitch C1 / C - C1)
+    const int VC1 = P.x2 ? P.C1 / 8 : VC;
+    const int VCs = tcol < VC1 ? VC1 : VC - VC1;
+    const uint4* base = tcol < VC1 ? reinterpret_cast<const uint4*>(P.x + (long long)n * P.S * (VC1 * 8)) + tcol
+                                   : reinterpret_cast<const uint4*>(P.x2 + (long long)n * P.S * (VCs * 8)) + (tcol - VC1);
     for (int r = r0 + trow; r < r1; r += 4 * rpp) {   // four row vectors in flight per thread
       uint4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (r + u * rpp < r1) v[u] = base[(long long)(r + u * rpp) * VC];
+        if (r + u * rpp < r1) v[u] = base[(long long)(r + u * rpp) * VCs];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (r + u * rpp >= r1) break;
@@ -596,12 +602,15 @@ __global__ void __launch_bounds__(512) gn_apply_rows_kernel(const GnNhwcParams P
     }
   }
   const int r0 = chunk * P.rows_per_chunk, r1 = min(P.S, r0 + P.rows_per_chunk);
-  const uint4* src = reinterpret_cast<const uint4*>(P.x + (long long)n * P.S * P.C) + tcol;
+  const int VC1 = P.x2 ? P.C1 / 8 : VC;
+  const int VCs = tcol < VC1 ? VC1 : VC - VC1;
+  const uint4* src = tcol < VC1 ? reinterpret_cast<const uint4*>(P.x + (long long)n * P.S * (VC1 * 8)) + tcol
+                                : reinterpret_cast<const uint4*>(P.x2 + (long long)n * P.S * (VCs * 8)) + (tcol - VC1);
   for (int r = r0 + trow; r < r1; r += 4 * rpp) {   // four row vectors in flight per thread
     uint4 xv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (r + u * rpp < r1) xv[u] = src[(long long)(r + u * rpp) * VC];
+      if (r + u * rpp < r1) xv[u] = src[(long long)(r + u * rpp) * VCs];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int rr = r + u * rpp;

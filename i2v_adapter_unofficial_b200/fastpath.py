@@ -359,52 +359,124 @@ def _is_silu(fn) -> bool:
     return isinstance(fn, nn.SiLU) or fn is F.silu
 
 
+def _resnet_simple(module: nn.Module, x: torch.Tensor, temb) -> bool:
+    """The ResnetBlock2D configurations the channels-last forward below covers (everything SD1.5 uses)."""
+    return (_fast_ok(x, module) and temb is not None and _nhwc_ok(x, module.norm1)
+            and isinstance(module.norm2, nn.GroupNorm) and module.norm2.affine
+            and _is_silu(getattr(module, "nonlinearity", None))
+            and getattr(module, "time_emb_proj", None) is not None
+            and getattr(module, "time_embedding_norm", "default") in (None, "default")
+            and not getattr(module, "up", False) and not getattr(module, "down", False)
+            and getattr(module, "upsample", None) is None and getattr(module, "downsample", None) is None
+            and getattr(module.dropout, "p", 0.0) == 0.0 and module.conv1.out_channels % 8 == 0
+            and isinstance(module.conv1, nn.Conv2d) and isinstance(module.conv2, nn.Conv2d)
+            and module.conv1.padding_mode == "zeros" and module.conv2.padding_mode == "zeros"
+            and module.conv1.out_channels <= 4096)
+
+
+def _pair_ok(module: nn.Module, x: torch.Tensor, x2: torch.Tensor, temb) -> bool:
+    """(hidden, skip) pair an up block would concatenate: the resnet can read the two tensors in place when its
+    shortcut is a 1x1 convolution (it always is there: the concatenation changes the channel count)."""
+    cs = getattr(module, "conv_shortcut", None)
+    return (_resnet_simple(module, x, temb) and x2.is_cuda and x2.dtype == x.dtype and ops.is_channels_last(x2)
+            and x2.shape[0] == x.shape[0] and x2.shape[2:] == x.shape[2:] and x2.shape[1] % 8 == 0
+            and x.shape[1] + x2.shape[1] <= 4096 and (x.shape[1] + x2.shape[1]) % module.norm1.num_groups == 0
+            and isinstance(cs, nn.Conv2d) and cs.kernel_size == (1, 1) and cs.stride == (1, 1) and cs.padding == (0, 0)
+            and cs.groups == 1 and cs.in_channels == x.shape[1] + x2.shape[1])
+
+
+def _resnet_forward_nhwc(module: nn.Module, x: torch.Tensor, temb: torch.Tensor,
+                         x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ResnetBlock2D on channels-last activations; with ``x2`` the input is ``torch.cat([x, x2], 1)`` read in place."""
+    n1, n2 = module.norm1, module.norm2
+    c1, c2 = module.conv1, module.conv2
+    h = ops.group_norm_nhwc(x, n1.weight, n1.bias, n1.num_groups, n1.eps, 1, silu=True, x2=x2)
+    # cuDNN applies a convolution bias as a separate broadcast-add pass; both biases of the block are per-channel
+    # constants that the next bandwidth kernel can carry instead: conv1's joins the time-embedding term of norm2,
+    # conv2's the residual add
+    h = F.conv2d(h, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
+    t = module.time_emb_proj(F.silu(temb))
+    if c1.bias is not None:
+        t = t + c1.bias
+    if not ops.is_channels_last(h):
+        h = h.contiguous(memory_format=torch.channels_last)
+    h = ops.group_norm_nhwc(h, n2.weight, n2.bias, n2.num_groups, n2.eps, 1, silu=True, add=t)
+    h = F.conv2d(h, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
+    cs = getattr(module, "conv_shortcut", None)
+    bias = c2.bias
+    if x2 is not None:
+        # 1x1 shortcut convolution of the concatenation = two token GEMMs on the two sources (channels-last rows)
+        N, Ca, hh, ww = x.shape
+        Cb = x2.shape[1]
+        wmat = cs.weight.reshape(cs.out_channels, Ca + Cb)
+        xa = x.permute(0, 2, 3, 1).reshape(N * hh * ww, Ca)
+        xb = x2.permute(0, 2, 3, 1).reshape(N * hh * ww, Cb)
+        sc = torch.mm(xa, wmat[:, :Ca].t())
+        sc.addmm_(xb, wmat[:, Ca:].t())
+        x = sc.view(N, hh, ww, cs.out_channels).permute(0, 3, 1, 2)
+        if cs.bias is not None:
+            bias = cs.bias if bias is None else bias + cs.bias
+    elif cs is not None:
+        if isinstance(cs, nn.Conv2d) and cs.padding_mode == "zeros" and ops.is_channels_last(h):
+            # the shortcut convolution's bias rides in the same residual pass as conv2's
+            x = F.conv2d(x, cs.weight, None, cs.stride, cs.padding, cs.dilation, cs.groups)
+            if cs.bias is not None:
+                bias = cs.bias if bias is None else bias + cs.bias
+        else:
+            x = cs(x)
+    if ops.is_channels_last(x) and ops.is_channels_last(h):
+        out = ops.nhwc_add(x, h, bias)             # x + h + bias[c] in one pass
+    else:
+        out = x + (h if bias is None else h + bias[None, :, None, None])
+    osf = getattr(module, "output_scale_factor", 1.0)
+    return out if osf == 1.0 else out / osf
+
+
 def _make_resnet_forward(module: nn.Module, original: Callable):
     @functools.wraps(original)
     def forward(x, temb=None, *args, **kwargs):
-        simple = (_fast_ok(x, module) and temb is not None and _nhwc_ok(x, module.norm1)
-                  and isinstance(module.norm2, nn.GroupNorm) and module.norm2.affine
-                  and _is_silu(getattr(module, "nonlinearity", None))
-                  and getattr(module, "time_emb_proj", None) is not None
-                  and getattr(module, "time_embedding_norm", "default") in (None, "default")
-                  and not getattr(module, "up", False) and not getattr(module, "down", False)
-                  and getattr(module, "upsample", None) is None and getattr(module, "downsample", None) is None
-                  and getattr(module.dropout, "p", 0.0) == 0.0 and module.conv1.out_channels % 8 == 0
-                  and isinstance(module.conv1, nn.Conv2d) and isinstance(module.conv2, nn.Conv2d)
-                  and module.conv1.padding_mode == "zeros" and module.conv2.padding_mode == "zeros"
-                  and module.conv1.out_channels <= 4096)
-        if not simple:
+        if not _resnet_simple(module, x, temb):
             return original(x, temb, *args, **kwargs)
-        n1, n2 = module.norm1, module.norm2
-        c1, c2 = module.conv1, module.conv2
-        h = ops.group_norm_nhwc(x, n1.weight, n1.bias, n1.num_groups, n1.eps, 1, silu=True)
-        # cuDNN applies a convolution bias as a separate broadcast-add pass; both biases of the block are per-channel
-        # constants that the next bandwidth kernel can carry instead: conv1's joins the time-embedding term of norm2,
-        # conv2's the residual add
-        h = F.conv2d(h, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
-        t = module.time_emb_proj(F.silu(temb))
-        if c1.bias is not None:
-            t = t + c1.bias
-        if not ops.is_channels_last(h):
-            h = h.contiguous(memory_format=torch.channels_last)
-        h = ops.group_norm_nhwc(h, n2.weight, n2.bias, n2.num_groups, n2.eps, 1, silu=True, add=t)
-        h = F.conv2d(h, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
-        cs = getattr(module, "conv_shortcut", None)
-        bias = c2.bias
-        if cs is not None:
-            if isinstance(cs, nn.Conv2d) and cs.padding_mode == "zeros" and ops.is_channels_last(h):
-                # the shortcut convolution's bias rides in the same residual pass as conv2's
-                x = F.conv2d(x, cs.weight, None, cs.stride, cs.padding, cs.dilation, cs.groups)
-                if cs.bias is not None:
-                    bias = cs.bias if bias is None else bias + cs.bias
+        return _resnet_forward_nhwc(module, x, temb)
+
+    return forward
+
+
+def _make_upblock_forward(module: nn.Module, original: Callable, cross: bool):
+    """CrossFrameAttnUpBlockMotion (reference unet_motion_cross_frame_attn.py:439-529) / UpBlockMotion: the same
+    sequencing, but ``torch.cat([hidden_states, res_hidden_states], dim=1)`` (:457) is not materialised -- the resnet's
+    GroupNorm and shortcut convolution read the two tensors in place."""
+    @functools.wraps(original)
+    def forward(hidden_states, res_hidden_states_tuple, temb=None, *args, **kwargs):
+        names = (("enable_cross_frame_attn", "encoder_hidden_states", "cross_attention_kwargs", "upsample_size",
+                  "attention_mask", "encoder_attention_mask", "num_frames") if cross
+                 else ("upsample_size", "scale", "num_frames"))
+        if len(args) > len(names) or not set(kwargs) <= set(names):
+            return original(hidden_states, res_hidden_states_tuple, temb, *args, **kwargs)
+        kw = dict(zip(names, args))
+        kw.update(kwargs)
+        num_frames = kw.get("num_frames", 1)
+        layers = (zip(module.resnets, module.attentions, module.motion_modules) if cross
+                  else zip(module.resnets, [None] * len(module.resnets), module.motion_modules))
+        for resnet, attn, motion_module in layers:
+            res = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            if "forward" in resnet.__dict__ and _pair_ok(resnet, hidden_states, res, temb):
+                hidden_states = _resnet_forward_nhwc(resnet, hidden_states, temb, res)
             else:
-                x = cs(x)
-        if ops.is_channels_last(x) and ops.is_channels_last(h):
-            out = ops.nhwc_add(x, h, bias)             # x + h + bias[c] in one pass
-        else:
-            out = x + (h if c2.bias is None else h + c2.bias[None, :, None, None])
-        osf = getattr(module, "output_scale_factor", 1.0)
-        return out if osf == 1.0 else out / osf
+                hidden_states = resnet(torch.cat([hidden_states, res], dim=1), temb)
+            if attn is not None:
+                hidden_states = attn(hidden_states, enable_cross_frame_attn=kw.get("enable_cross_frame_attn", False),
+                                     num_frames=num_frames, encoder_hidden_states=kw.get("encoder_hidden_states"),
+                                     cross_attention_kwargs=kw.get("cross_attention_kwargs"),
+                                     attention_mask=kw.get("attention_mask"),
+                                     encoder_attention_mask=kw.get("encoder_attention_mask"),
+                                     return_dict=False)[0]                                       # reference :499-508
+            hidden_states = motion_module(hidden_states, num_frames=num_frames)[0]
+        if module.upsamplers is not None:
+            for u in module.upsamplers:
+                hidden_states = u(hidden_states, kw.get("upsample_size"))
+        return hidden_states
 
     return forward
 
@@ -517,6 +589,10 @@ def install_fast_forwards(root: nn.Module) -> List[Callable[[], None]]:
             patch(module, _make_temporal_forward(module, module.forward))
         elif name == "ResnetBlock2D":
             patch(module, _make_resnet_forward(module, module.forward))
+        elif name == "CrossFrameAttnUpBlockMotion" and hasattr(module, "motion_modules"):
+            patch(module, _make_upblock_forward(module, module.forward, True))
+        elif name == "UpBlockMotion" and hasattr(module, "motion_modules"):
+            patch(module, _make_upblock_forward(module, module.forward, False))
         elif name == "Upsample2D":
             patch(module, _make_upsample_forward(module, module.forward))
         elif name == "Downsample2D":

@@ -337,28 +337,36 @@ def is_channels_last(x: torch.Tensor) -> bool:
 
 def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, eps: float,
                     frames_per_stat: int = 1, silu: bool = False, add: Optional[torch.Tensor] = None,
-                    to_positions: bool = False) -> torch.Tensor:
+                    to_positions: bool = False, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GroupNorm of a channels-last activation x (N, C, h, w) [+ per-(n, c) ``add`` before, + SiLU after].
 
     Returns a channels-last (N, C, h, w) tensor, or with ``to_positions`` the motion module's [N/F * h*w, F, C]
-    token layout (statistics shared by the F = ``frames_per_stat`` frames of a video either way)."""
+    token layout (statistics shared by the F = ``frames_per_stat`` frames of a video either way).  With ``x2`` the
+    input is the channel concatenation ``torch.cat([x, x2], 1)``, read from the two tensors in place."""
     if not (x.is_cuda and x.dtype == torch.bfloat16 and is_channels_last(x)):
         raise RuntimeError("group_norm_nhwc: needs a CUDA bf16 channels-last tensor (no CPU fallback)")
     dev = x.device
     N, C, h, w = x.shape
+    C1 = C
+    if x2 is not None:
+        if not (x2.is_cuda and x2.dtype == x.dtype and is_channels_last(x2) and x2.shape[0] == N
+                and x2.shape[2:] == x.shape[2:] and C1 % 8 == 0 and x2.shape[1] % 8 == 0):
+            raise RuntimeError("group_norm_nhwc: the second source must be a matching channels-last tensor, C % 8 == 0")
+        C = C1 + x2.shape[1]
     S, fg = h * w, frames_per_stat
     lib = _lib.load()
     scratch = torch.empty((int(lib.i2v_gn_nhwc_scratch_floats(N, groups)),), dtype=torch.float32, device=dev)
     if to_positions:
         out = torch.empty((N // fg * S, fg, C), dtype=x.dtype, device=dev)
     else:
-        out = torch.empty_like(x)  # preserves channels_last
+        out = torch.empty((N, C, h, w), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
     if add is not None:
         add = add.to(dtype=x.dtype).reshape(N, C).contiguous()
     with _on_device(dev):
-        _lib.check(lib.i2v_gn_nhwc(x.data_ptr(), add.data_ptr() if add is not None else None, weight.data_ptr(),
-                                   bias.data_ptr(), out.data_ptr(), scratch.data_ptr(), N, S, C, groups, fg, float(eps),
-                                   int(silu), int(to_positions), _stream(dev)))
+        _lib.check(lib.i2v_gn_nhwc_cat(x.data_ptr(), None if x2 is None else x2.data_ptr(), C1,
+                                       add.data_ptr() if add is not None else None, weight.data_ptr(), bias.data_ptr(),
+                                       out.data_ptr(), scratch.data_ptr(), N, S, C, groups, fg, float(eps), int(silu),
+                                       int(to_positions), _stream(dev)))
     return out
 
 

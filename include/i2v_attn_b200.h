@@ -177,6 +177,11 @@ int i2v_untranspose_residual(const void* y, const void* res, void* out, int N, i
 long long i2v_gn_nhwc_scratch_floats(int N, int G);
 int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, void* out, float* scratch,
                 int N, int S, int C, int G, int fg, float eps, int silu, int perm, void* stream);
+/* i2v_gn_nhwc_cat: the same on the virtual channel concatenation of two channels-last activations x [N, S, C1] and
+ *   x2 [N, S, C - C1] (x2 == NULL: plain i2v_gn_nhwc): the up blocks' torch.cat([hidden_states, res_hidden_states], 1)
+ *   ahead of their ResnetBlock2D (src/models/unet_motion_cross_frame_attn.py:457) is never written to memory. */
+int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, const void* w, const void* b, void* out,
+                    float* scratch, int N, int S, int C, int G, int fg, float eps, int silu, int perm, void* stream);
 
 /* out[n, s, :] = y[(v*S + s)*fg + f, :] + res[n, s, :] with n = v*fg + f: the motion module's way back to the
  * frame-major channels-last activation, fused with its residual add. */

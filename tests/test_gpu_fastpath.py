@@ -392,3 +392,46 @@ def test_sampler_fast_paths_match_the_modules():
             handle.uninstall()
         assert out.shape == ref.shape
         assert (out - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(4, 320, 320, 16, 16, 32), (2, 1280, 640, 8, 8, 32), (3, 640, 320, 12, 12, 32)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_group_norm_nhwc_two_sources_equals_concatenation(case, silu):
+    N, C1, C2, h, w_, G = case
+    cl = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    a, b = cl(_rand((N, C1, h, w_), 61, 1.5, 0.3)), cl(_rand((N, C2, h, w_), 62, 0.7, -0.2))
+    w, bias = _rand((C1 + C2,), 63, 0.3, 1.0).to(DEV), _rand((C1 + C2,), 64, 0.3).to(DEV)
+    cat = cl(torch.cat([a, b], 1))
+    ref = ops.group_norm_nhwc(cat, w, bias, G, 1e-5, 1, silu=silu)
+    out = ops.group_norm_nhwc(a, w, bias, G, 1e-5, 1, silu=silu, x2=b)
+    assert ops.is_channels_last(out) and out.shape == ref.shape
+    assert (out.float() - ref.float()).abs().max().item() <= 2e-2   # channel sums accumulate in a different order
+
+
+def test_up_block_without_concatenation_matches_module():
+    """CrossFrameAttnUpBlockMotion fast forward (GroupNorm and shortcut convolution read hidden and skip in place)
+    against the same block with processors only."""
+    from i2v_adapter_unofficial_b200.hostmodel import CrossFrameAttnUpBlockMotion
+
+    torch.manual_seed(9)
+    blk = CrossFrameAttnUpBlockMotion(in_channels=320, out_channels=320, prev_output_channel=640, temb_channels=1280,
+                                      num_layers=3, resnet_eps=1e-5, resnet_groups=32, num_attention_heads=8,
+                                      cross_attention_dim=768, add_upsample=False, temporal_num_attention_heads=8,
+                                      temporal_max_seq_length=32).eval()
+    randomize_zero_init(blk)
+    Fr, hw = 4, 16
+    x = torch.randn(Fr, 640, hw, hw)
+    skips = tuple(torch.randn(Fr, c, hw, hw) for c in (320, 320, 320))
+    temb, ctx = torch.randn(Fr, 1280), torch.randn(Fr, 77, 768)
+    blk = blk.to(DEV, torch.bfloat16)
+    args = [t.to(DEV, torch.bfloat16) for t in (x, temb, ctx)]
+    sk = tuple(t.to(DEV, torch.bfloat16) for t in skips)
+    outs = {}
+    for fast in (False, True):
+        handle = install(blk, fast_path=fast)
+        with torch.no_grad():
+            outs[fast] = blk(args[0], sk, args[1], enable_cross_frame_attn=True, encoder_hidden_states=args[2],
+                             num_frames=Fr).float().cpu()
+        handle.uninstall()
+    cos = F.cosine_similarity(outs[True].flatten(), outs[False].flatten(), dim=0).item()
+    assert cos >= 0.9995, cos
