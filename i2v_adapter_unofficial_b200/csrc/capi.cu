@@ -823,9 +823,9 @@ int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, lo
     attr_set[dev & 63] = true;
   }
   const long long tiles = (long long)P.m_tiles * P.n_tiles;
-  // tuning key 7: 1 = single-CTA kernel, 2 = clusters even where they are not the default
+  // CTA pairs (2-SM MMA) wherever there are two row blocks; tuning key 7 = 1: single-CTA kernel
   const int ncl = max_clusters[dev & 63] < di->sms / 2 ? max_clusters[dev & 63] : di->sms / 2;
-  const bool use_cluster = g_tuning[7] != 1 && ncl > 0 && P.m_tiles >= 2 && (K <= 640 || g_tuning[7] == 2);
+  const bool use_cluster = g_tuning[7] != 1 && ncl > 0 && P.m_tiles >= 2;
   if (use_cluster) {
     const long long units = (long long)((P.m_tiles + 1) / 2) * P.n_tiles;
     const long long clusters = units < ncl ? units : ncl;

@@ -15,11 +15,14 @@
 // columns), 16 epilogue warps (lane quarter x column group) that overlap tile i's GELU with tile i+1's MMAs.
 // Tiles are walked n-fastest, so the CTAs running at the same time share x row blocks through L2.
 //
-// CL = 2: thread-block clusters of two CTAs work on two row blocks of the same n-tile in lockstep and share the weight
-// operand: CTA 0 loads the hidden box, CTA 1 the gate box, each multicast into both CTAs' stage, so a CTA pulls 32 KB
-// instead of 48 KB per k-block through the L2 -> SM path (what bounds the single-CTA kernel at K = 320: 240 KB per
-// 128 x 256 x 320 tile, 10 TB/s over the chip).  A stage is free when both CTAs' MMAs have consumed it (the MMA
-// warps commit to both CTAs' empty barriers).
+// CL = 2: CTA pairs (clusters of two on one TPC) run the 2-SM MMA, tcgen05 cta_group::2, M = 256: the two CTAs own two
+// row blocks of the same n-tile, each loads its own x tile and HALF of the weight operand (CTA 0 the hidden box, CTA 1
+// the gate box) into its own shared memory, the leader CTA issues the MMAs for both and each CTA's TMEM receives its
+// 128 rows of the 256 x 256 accumulator.  Per k-block a CTA takes in and reads back 32 KB instead of 48 KB: the
+// single-CTA kernel is bound by exactly that (shared-memory bandwidth: 12 KB read + 12 KB written per k-step = 192 clk
+// against 128 clk of math; at K = 320 the L2 -> SM path), and the stages become small enough for a 6-deep ring.
+// Barriers: full[s] lives in the leader and counts both CTAs' TMA bytes; empty[s] / acc_full[b] exist in both CTAs and
+// get the leader's multicast commits; acc_empty[b] lives in the leader and takes both CTAs' epilogue warps.
 #pragma once
 #include <cuda.h>
 #include "ptx_sm100.cuh"
@@ -43,6 +46,9 @@ constexpr int kFfThreads = (kFfEpiWarps + 2) * 32; // epilogue warps, TMA warp, 
 constexpr int kFfABytes = 128 * 128;               // 128 rows x 64 bf16
 constexpr int kFfBBytes = 256 * 128;               // 256 rows x 64 bf16
 constexpr int kFfStageBytes = kFfABytes + kFfBBytes;
+constexpr int kFfPairStages = 6;                   // CL = 2: x tile + half of the weight tile per stage
+constexpr int kFfPairStageBytes = 2 * kFfABytes;
+static_assert(kFfPairStages * kFfPairStageBytes <= kFfStages * kFfStageBytes, "both variants share one smem size");
 constexpr int kFfBiasBytes = kFfEpiWarps * 64 * 4;  // per epilogue warp: fp32 biases of its 32 hidden + 32 gate columns
 constexpr int kFfSmemBytes = kFfStages * kFfStageBytes + 256 + kFfBiasBytes + 1024;
 
@@ -52,9 +58,11 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFfStages * kFfStageBytes);
+  constexpr int NST = CL == 2 ? kFfPairStages : kFfStages;
+  constexpr int STAGE_BYTES = CL == 2 ? kFfPairStageBytes : kFfStageBytes;
   uint64_t* bar_full = bars;                       // [stages]  TMA -> MMA
-  uint64_t* bar_empty = bars + kFfStages;          // [stages]  MMA -> TMA
-  uint64_t* bar_acc_full = bars + 2 * kFfStages;   // [2]       MMA -> epilogue
+  uint64_t* bar_empty = bars + kFfPairStages;      // [stages]  MMA -> TMA
+  uint64_t* bar_acc_full = bars + 2 * kFfPairStages;   // [2]       MMA -> epilogue
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2]       epilogue -> MMA (one arrival per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
   float* sm_bias = reinterpret_cast<float*>(smem + kFfStages * kFfStageBytes + 256);   // [epilogue warp][hidden 32 | gate 32]
@@ -68,17 +76,20 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   const long long u_begin = blockIdx.x / CL, u_step = gridDim.x / CL;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFfStages; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(bar_full + s, 1);
-      mbar_init(bar_empty + s, CL);
+      mbar_init(bar_empty + s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full + b, 1);
-      mbar_init(bar_acc_empty + b, kFfEpiWarps);
+      mbar_init(bar_acc_empty + b, CL * kFfEpiWarps);
     }
     mbar_fence_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) {
+    if (CL == 2) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&P.tm_x);
     tma_prefetch_desc(&P.tm_w);
@@ -96,48 +107,57 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
         const int nt = (int)(u % P.n_tiles);
         const int m0 = ((int)(u / P.n_tiles) * CL + (int)rank) * 128, n0 = nt * 128;
         for (int kb = 0; kb < kblocks; ++kb, ++g) {
-          const int s = g % kFfStages;
-          mbar_wait(bar_empty + s, ((g / kFfStages) & 1) ^ 1);
-          uint8_t* a = smem + s * kFfStageBytes;
-          mbar_arrive_expect_tx(bar_full + s, kFfStageBytes);
-          tma_load_2d(a, &P.tm_x, bar_full + s, kb * 64, m0, kEvictNormal);
+          const int s = g % NST;
+          mbar_wait(bar_empty + s, ((g / NST) & 1) ^ 1);
+          uint8_t* a = smem + s * STAGE_BYTES;
           if (CL == 1) {
+            mbar_arrive_expect_tx(bar_full + s, STAGE_BYTES);
+            tma_load_2d(a, &P.tm_x, bar_full + s, kb * 64, m0, kEvictNormal);
             tma_load_2d(a + kFfABytes, &P.tm_w, bar_full + s, kb * 64, n0, kEvictLast);
             tma_load_2d(a + kFfABytes + kFfABytes, &P.tm_w, bar_full + s, kb * 64, P.N + n0, kEvictLast);
-          } else {   // this CTA's half of the weight operand, delivered to both CTAs of the cluster
-            tma_load_2d_multicast(a + kFfABytes + rank * kFfABytes, &P.tm_w, bar_full + s, kb * 64,
-                                  (int)rank * P.N + n0, (uint16_t)0b11, kEvictLast);
+          } else {
+            // the leader's barrier collects the bytes of both CTAs' loads
+            if (rank == 0) mbar_arrive_expect_tx(bar_full + s, 2 * STAGE_BYTES);
+            tma_load_2d_pair(a, &P.tm_x, bar_full + s, kb * 64, m0, kEvictNormal);
+            tma_load_2d_pair(a + kFfABytes, &P.tm_w, bar_full + s, kb * 64, (int)rank * P.N + n0, kEvictLast);
           }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
-    const uint64_t desc0 = make_smem_desc_sw128(0, 16, 1024);
-    uint32_t g = 0;
-    int i = 0;
-    for (long long u = u_begin; u < units; u += u_step, ++i) {
-      const int b = i & 1;
-      mbar_wait(bar_acc_empty + b, ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
-      tc_fence_after();
-      for (int kb = 0; kb < kblocks; ++kb, ++g) {
-        const int s = g % kFfStages;
-        mbar_wait(bar_full + s, (g / kFfStages) & 1);
+    if (CL == 1 || rank == 0) {   // CTA pair: the leader issues for both
+      constexpr uint32_t idesc = make_idesc_bf16(CL == 2 ? 256 : 128, 256, 0, 0);
+      const uint64_t desc0 = make_smem_desc_sw128(0, 16, 1024);
+      uint32_t g = 0;
+      int i = 0;
+      for (long long u = u_begin; u < units; u += u_step, ++i) {
+        const int b = i & 1;
+        mbar_wait(bar_acc_empty + b, ((i >> 1) & 1) ^ 1);   // the epilogue warps have drained this accumulator buffer
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t aa = smem_u32(smem + s * kFfStageBytes) >> 4;
-          const uint32_t ba = aa + (kFfABytes >> 4);
+        for (int kb = 0; kb < kblocks; ++kb, ++g) {
+          const int s = g % NST;
+          mbar_wait(bar_full + s, (g / NST) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t aa = smem_u32(smem + s * STAGE_BYTES) >> 4;
+            const uint32_t ba = aa + (kFfABytes >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {   // 32 bytes per 16-column k-step inside the 128-byte swizzle row
-            const uint64_t da = desc0 | (uint64_t)((aa + kk * 2) & 0x3FFF);
-            const uint64_t db = desc0 | (uint64_t)((ba + kk * 2) & 0x3FFF);
-            umma_ss(tmem_base + b * 256, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {   // 32 bytes per 16-column k-step inside the 128-byte swizzle row
+              const uint64_t da = desc0 | (uint64_t)((aa + kk * 2) & 0x3FFF);
+              const uint64_t db = desc0 | (uint64_t)((ba + kk * 2) & 0x3FFF);
+              if (CL == 1) umma_ss(tmem_base + b * 256, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+              else umma_ss_pair(tmem_base + b * 256, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            }
+            if (CL == 1) {
+              tc_commit(bar_empty + s);
+              if (kb == kblocks - 1) tc_commit(bar_acc_full + b);
+            } else {
+              tc_commit_pair(bar_empty + s, (uint16_t)0b11);
+              if (kb == kblocks - 1) tc_commit_pair(bar_acc_full + b, (uint16_t)0b11);
+            }
           }
-          if (CL == 1) tc_commit(bar_empty + s);
-          else tc_commit_multicast(bar_empty + s, (uint16_t)0b11);
-          if (kb == kblocks - 1) tc_commit(bar_acc_full + b);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
@@ -195,7 +215,10 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
         *reinterpret_cast<uint4*>(P.out + row * P.ld + P.N) = make_uint4(0x00003F80u, 0u, 0u, 0u);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + b);
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(bar_acc_empty + b);
+        else mbar_arrive_cluster(bar_acc_empty + b, 0u);   // the leader's barrier
+      }
     }
   }
 
@@ -204,7 +227,8 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (CL == 2) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
