@@ -767,9 +767,9 @@ int i2v_geglu_ld_fwd(const void* x, void* y, long long rows, int D, int ld_out, 
 }
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix: dims (cols, rows), box (64, 128), 128-byte swizzle.
-static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols) {
+static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols, int pitch = 0) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)(pitch ? pitch : cols) * 2};
   cuuint32_t box[2] = {64, 128};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -798,6 +798,7 @@ int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, lo
   memset(&P, 0, sizeof(P));
   if ((rc = make_tmap_2d(&P.tm_x, x, rows, K))) return rc;
   if ((rc = make_tmap_2d(&P.tm_w, w, 2LL * N, K))) return rc;
+  if ((rc = make_tmap_2d(&P.tm_y, y, rows, N, ld_out))) return rc;   // the ones column (ld_out = N + 8) is written directly
   P.bias = (const __nv_bfloat16*)bias; P.out = (__nv_bfloat16*)y;
   P.rows = rows; P.N = N; P.K = K; P.ld = ld_out;
   P.m_tiles = (int)((rows + 127) / 128); P.n_tiles = N / 128;

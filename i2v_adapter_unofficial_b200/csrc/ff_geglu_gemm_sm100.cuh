@@ -33,6 +33,7 @@ namespace i2v {
 struct FfGegluParams {
   CUtensorMap tm_x;            // x [rows, K] bf16: dims (K, rows), box (64, 128), 128B swizzle
   CUtensorMap tm_w;            // W [2N, K] bf16:   dims (K, 2N),  box (64, 128)
+  CUtensorMap tm_y;            // y [rows, ld] bf16: dims (ld, rows), box (64, 128): the epilogue's tiled stores
   const __nv_bfloat16* bias;   // [2N] or nullptr
   __nv_bfloat16* out;          // [rows, ld]
   long long rows;
@@ -40,24 +41,28 @@ struct FfGegluParams {
   int m_tiles, n_tiles;
 };
 
-constexpr int kFfStages = 4;
+constexpr int kFfStages = 3;
 constexpr int kFfEpiWarps = 16;                    // lane quarter x group of 32 output columns
 constexpr int kFfThreads = (kFfEpiWarps + 2) * 32; // epilogue warps, TMA warp, MMA warp
 constexpr int kFfABytes = 128 * 128;               // 128 rows x 64 bf16
 constexpr int kFfBBytes = 256 * 128;               // 256 rows x 64 bf16
 constexpr int kFfStageBytes = kFfABytes + kFfBBytes;
-constexpr int kFfPairStages = 6;                   // CL = 2: x tile + half of the weight tile per stage
+constexpr int kFfPairStages = 5;                   // CL = 2: x tile + half of the weight tile per stage
 constexpr int kFfPairStageBytes = 2 * kFfABytes;
-static_assert(kFfPairStages * kFfPairStageBytes <= kFfStages * kFfStageBytes, "both variants share one smem size");
+constexpr int kFfRingBytes = kFfPairStages * kFfPairStageBytes;   // 160 KB (>= the single-CTA ring, 144 KB)
+static_assert(kFfStages * kFfStageBytes <= kFfRingBytes, "both variants share one smem layout");
+constexpr int kFfOutBytes = 2 * kFfABytes;          // output tile staged for the tiled store: two [128 rows][64 bf16] halves
 constexpr int kFfBiasBytes = kFfEpiWarps * 64 * 4;  // per epilogue warp: fp32 biases of its 32 hidden + 32 gate columns
-constexpr int kFfSmemBytes = kFfStages * kFfStageBytes + 256 + kFfBiasBytes + 1024;
+constexpr int kFfSmemBytes = kFfRingBytes + kFfOutBytes + 256 + kFfBiasBytes + 1024;
+static_assert(kFfSmemBytes <= 227 * 1024, "smem budget");
 
 template <int CL>
 __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __grid_constant__ FfGegluParams P) {
   static_assert(CL == 1 || CL == 2, "cluster size");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFfStages * kFfStageBytes);
+  uint8_t* sm_out = smem + kFfRingBytes;           // [2][128 rows][128 B], 128-byte swizzle (what the store's tensor map expects)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_out + kFfOutBytes);
   constexpr int NST = CL == 2 ? kFfPairStages : kFfStages;
   constexpr int STAGE_BYTES = CL == 2 ? kFfPairStageBytes : kFfStageBytes;
   uint64_t* bar_full = bars;                       // [stages]  TMA -> MMA
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   uint64_t* bar_acc_full = bars + 2 * kFfPairStages;   // [2]       MMA -> epilogue
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2]       epilogue -> MMA (one arrival per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
-  float* sm_bias = reinterpret_cast<float*>(smem + kFfStages * kFfStageBytes + 256);   // [epilogue warp][hidden 32 | gate 32]
+  float* sm_bias = reinterpret_cast<float*>(sm_out + kFfOutBytes + 256);   // [epilogue warp][hidden 32 | gate 32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kTmaWarp = kFfEpiWarps, kMmaWarp = kFfEpiWarps + 1;
@@ -93,6 +98,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&P.tm_x);
     tma_prefetch_desc(&P.tm_w);
+    tma_prefetch_desc(&P.tm_y);
   }
   tc_fence_before();
   __syncthreads();
@@ -171,16 +177,23 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
       const int nt = (int)(u % P.n_tiles);
       const long long row = ((u / P.n_tiles) * CL + rank) * 128 + quarter * 32 + lane;
       const int n0 = nt * 128 + half * CW;
-      mbar_wait(bar_acc_full + b, (i >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tm = tmem_base + lane_addr + b * 256 + half * CW;
-      __nv_bfloat16* orow = P.out + row * P.ld + n0;
-      // this warp's biases as fp32 pairs in its own shared-memory slot (no cross-warp synchronisation)
+      // this warp's biases as fp32 pairs in its own shared-memory slot (no cross-warp synchronisation), fetched
+      // before the wait for the accumulator so that the global-load latency hides under the tile's MMAs
       float* wb = sm_bias + warp * 64;
       __syncwarp();   // the previous tile's reads of the slot are done
       wb[lane] = P.bias ? __bfloat162float(P.bias[n0 + lane]) : 0.f;
       wb[32 + lane] = P.bias ? __bfloat162float(P.bias[P.N + n0 + lane]) : 0.f;
       __syncwarp();
+      mbar_wait(bar_acc_full + b, (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tm = tmem_base + lane_addr + b * 256 + half * CW;
+      // the staging tile is free once the previous tile's stores have read it (the issuing thread waits, then everyone
+      // passes this barrier)
+      if (threadIdx.x == 0 && i > 0) tma_store_wait_read();
+      named_bar_sync(1, kFfEpiWarps * 32);
+      const int trow = quarter * 32 + lane;                     // row of the tile
+      uint8_t* srow = sm_out + (half * CW / 64) * kFfABytes + trow * 128;   // this row in its 64-column half
+      const int c16 = (half * CW % 64) / 8;                     // first 16-byte chunk of this warp's columns in the row
       // chunks of 16 columns, software-pipelined: the TMEM loads of chunk ch + 1 are in flight under the GELUs of ch
       uint32_t h[2][16], gt[2][16];
       tmem_ld_x16(tm, h[0]);
@@ -202,14 +215,12 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
           const uint64_t h2 = f2_add(f2_pack(__uint_as_float(hc[2 * k]), __uint_as_float(hc[2 * k + 1])), bh2[k]);
           const uint64_t g2 = f2_add(f2_pack(__uint_as_float(gc[2 * k]), __uint_as_float(gc[2 * k + 1])), bg2[k]);
           float r0, r1;
-          f2_unpack(geglu_pair(h2, g2), r0, r1);
+          f2_unpack(geglu_pair_poly(h2, g2), r0, r1);
           o[k] = bf16_pack(r0, r1);
         }
-        if (row < P.rows) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + ch * 16);
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        }
+        // 128-byte swizzle: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
+        *reinterpret_cast<uint4*>(srow + (((c16 + 2 * ch) ^ (trow & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(srow + (((c16 + 2 * ch + 1) ^ (trow & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
       }
       if (P.ld > P.N && nt == 0 && half == 0 && row < P.rows)   // ones column for the next GEMM's deferred bias
         *reinterpret_cast<uint4*>(P.out + row * P.ld + P.N) = make_uint4(0x00003F80u, 0u, 0u, 0u);
@@ -219,9 +230,18 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
         if (CL == 1) mbar_arrive(bar_acc_empty + b);
         else mbar_arrive_cluster(bar_acc_empty + b, 0u);   // the leader's barrier
       }
+      fence_proxy_async_smem();                   // generic-proxy writes of the staging tile -> the store's async proxy
+      named_bar_sync(2, kFfEpiWarps * 32);
+      if (threadIdx.x == 0) {                     // rows past the end of y are clipped by the tensor map
+        const int m0 = (int)(row - trow);
+        tma_store_2d(&P.tm_y, sm_out, nt * 128, m0);
+        tma_store_2d(&P.tm_y, sm_out + kFfABytes, nt * 128 + 64, m0);
+        tma_store_commit();
+      }
     }
   }
 
+  if (threadIdx.x == 0) tma_store_wait_all();     // the last tile's stores have left shared memory and are complete
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers

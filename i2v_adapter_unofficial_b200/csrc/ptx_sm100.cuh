@@ -137,6 +137,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
         "l"(cache_hint)
       : "memory");
 }
+// Tiled store shared -> global (bulk async-group completion): the issuing thread commits a group and, before the
+// shared-memory source is overwritten, waits until the group has been read.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // Multicast flavour: the box lands at the same shared-memory offset of every CTA in `cta_mask` and completes bytes on the
 // mbarrier at the same offset of each of them.
 __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
