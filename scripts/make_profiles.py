@@ -93,10 +93,25 @@ def main():
                               "Decoupled text (77) + image (4) cross-attention at the C2 level-0 size (32 frames x 4096 "
                               "queries x 8 heads x d=40; reads Q and writes O once: 167.8 MB algorithmic bytes per launch), "
                               "launched by `scripts/perf_ip_one.py`.  Expected before measuring: HBM-bound by design, in "
-                              "practice limited by the instruction count of the two-segment softmax at 2-3 resident warps "
-                              "per sub-partition.")
+                              "practice limited by dependent mma.sync chains and the two-segment softmax at 72 registers per "
+                              "thread (three CTAs per SM); instantiation with compile-time token counts (77 + 4).")
         open(os.path.join(OUT, f"{TAG}_ip_attn_l0.md"), "w").write(i_txt)
         print("ip:", i.get("gpu__time_duration.sum"), "dram r/w", i.get("dram__bytes_read.sum"), i.get("dram__bytes_write.sum"))
+    ff_rep = os.path.join(SRC, "prof_ff.ncu-rep")
+    if os.path.exists(ff_rep):
+        f_txt, ff = ncu_digest(ff_rep, f"Feed-forward projection + GEGLU GEMM, level 0 ({TAG})",
+                               "`ff_geglu_gemm_kernel<2>` (CTA pairs, tcgen05 cta_group::2) at the C2 level-0 shape: "
+                               "131072 x 320 -> 1280 (+ ones column), 215 GFLOP and 84 MB in / 335 MB out algorithmic per "
+                               "launch, launched by `scripts/perf_ff_one.py`.  Expected before measuring: tensor-pipe "
+                               "bound in the mainloop (the epilogue-free kernel runs 130 us = 1650 TFLOP/s), the epilogue "
+                               "(TMEM -> GELU -> staged TMA store) not fully hidden at K = 320.")
+        open(os.path.join(OUT, f"{TAG}_ff_geglu_gemm_l0.md"), "w").write(f_txt)
+        print("ff:", ff.get("gpu__time_duration.sum"), "dram r/w", ff.get("dram__bytes_read.sum"), ff.get("dram__bytes_write.sum"))
+    n8 = os.path.join(SRC, "bench_n8.log")
+    if os.path.exists(n8):
+        line = open(n8).read().strip().splitlines()[-1]
+        json.loads(line)
+        open(os.path.join(OUT, f"{TAG}_bench_n8.json"), "w").write(line + "\n")
     open(os.path.join(OUT, f"{TAG}_dense_attn_l0.md"), "w").write(d_txt)
     open(os.path.join(OUT, f"{TAG}_temporal_attn_l0.md"), "w").write(t_txt)
     bench = open(os.path.join(SRC, "bench.log")).read().strip().splitlines()[-1]
