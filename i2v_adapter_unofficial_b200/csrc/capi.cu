@@ -809,6 +809,7 @@ int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, lo
   if (!attr_set[dev & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(i2v::ff_geglu_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kFfSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(i2v::ff_geglu_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kFfSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(i2v::ff_geglu_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kFfSmemBytes));
     // how many 2-CTA clusters of this kernel the device can hold at once (persistent grid: one wave)
     cudaLaunchConfig_t probe = {};
     probe.gridDim = dim3((unsigned)(di->sms / 2 * 2));
@@ -839,7 +840,9 @@ int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, lo
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, i2v::ff_geglu_gemm_kernel<2>, P));
+    // K <= 320: x tile resident, weight halves streamed (tuning key 7 = 2: streaming variant)
+    if (K / 64 <= i2v::kFfXresKBlocks && g_tuning[7] != 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, i2v::ff_geglu_gemm_kernel<2, true>, P));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, i2v::ff_geglu_gemm_kernel<2, false>, P));
   } else {
     const long long grid = tiles < di->sms ? tiles : di->sms;
     i2v::ff_geglu_gemm_kernel<1><<<(unsigned)grid, i2v::kFfThreads, i2v::kFfSmemBytes, (cudaStream_t)stream>>>(P);

@@ -23,6 +23,11 @@
 // against 128 clk of math; at K = 320 the L2 -> SM path), and the stages become small enough for a 6-deep ring.
 // Barriers: full[s] lives in the leader and counts both CTAs' TMA bytes; empty[s] / acc_full[b] exist in both CTAs and
 // get the leader's multicast commits; acc_empty[b] lives in the leader and takes both CTAs' epilogue warps.
+//
+// XRES (CL = 2, K <= 320: SD1.5 level 0, where a tile is only five k-blocks and the kernel is bound by TMA latency
+// against the bytes a CTA can keep in flight): every pair owns a contiguous range of the (row pair, n-tile) order, so
+// consecutive units share their x rows; the CTA's whole 128 x K x tile stays resident (80 KB) and only its half of the
+// weight tile streams through the ring -- half the bytes per tile.
 #pragma once
 #include <cuda.h>
 #include "ptx_sm100.cuh"
@@ -56,20 +61,27 @@ constexpr int kFfBiasBytes = kFfEpiWarps * 64 * 4;  // per epilogue warp: fp32 b
 constexpr int kFfSmemBytes = kFfRingBytes + kFfOutBytes + 256 + kFfBiasBytes + 1024;
 static_assert(kFfSmemBytes <= 227 * 1024, "smem budget");
 
-template <int CL>
+constexpr int kFfXresKBlocks = 5;                  // XRES: resident x tile of up to 5 k-blocks
+constexpr int kFfXresStages = (kFfRingBytes - kFfXresKBlocks * kFfABytes) / kFfABytes;   // weight-half ring behind it
+
+template <int CL, bool XRES = false>
 __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __grid_constant__ FfGegluParams P) {
   static_assert(CL == 1 || CL == 2, "cluster size");
+  static_assert(!XRES || CL == 2, "the x-resident variant is a CTA-pair kernel");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sm_out = smem + kFfRingBytes;           // [2][128 rows][128 B], 128-byte swizzle (what the store's tensor map expects)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_out + kFfOutBytes);
-  constexpr int NST = CL == 2 ? kFfPairStages : kFfStages;
-  constexpr int STAGE_BYTES = CL == 2 ? kFfPairStageBytes : kFfStageBytes;
+  constexpr int NST = XRES ? kFfXresStages : CL == 2 ? kFfPairStages : kFfStages;
+  constexpr int STAGE_BYTES = XRES ? kFfABytes : CL == 2 ? kFfPairStageBytes : kFfStageBytes;
+  uint8_t* ring = smem + (XRES ? kFfXresKBlocks * kFfABytes : 0);   // XRES: the resident x tile comes first
   uint64_t* bar_full = bars;                       // [stages]  TMA -> MMA
   uint64_t* bar_empty = bars + kFfPairStages;      // [stages]  MMA -> TMA
   uint64_t* bar_acc_full = bars + 2 * kFfPairStages;   // [2]       MMA -> epilogue
   uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2]       epilogue -> MMA (one arrival per epilogue warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_x_full = bar_acc_empty + 2;        // [1]       XRES: the resident x tile landed (leader, both CTAs' bytes)
+  uint64_t* bar_x_free = bar_x_full + 1;           // [1]       XRES: every MMA on the old x tile retired (both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_x_free + 1);
   float* sm_bias = reinterpret_cast<float*>(sm_out + kFfOutBytes + 256);   // [epilogue warp][hidden 32 | gate 32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,13 +90,19 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   // work unit = CL row blocks (2 u + rank of the CTA in its cluster) of one n-tile; units are walked n-fastest
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   const long long units = (long long)((P.m_tiles + CL - 1) / CL) * P.n_tiles;
-  const long long u_begin = blockIdx.x / CL, u_step = gridDim.x / CL;
+  const long long n_groups = gridDim.x / CL;
+  const long long per = (units + n_groups - 1) / n_groups;
+  const long long u_begin = XRES ? min(units, (long long)(blockIdx.x / CL) * per) : blockIdx.x / CL;
+  const long long u_end = XRES ? min(units, u_begin + per) : units;
+  const long long u_step = XRES ? 1 : n_groups;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(bar_full + s, 1);
       mbar_init(bar_empty + s, 1);
     }
+    mbar_init(bar_x_full, 1);
+    mbar_init(bar_x_free, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full + b, 1);
       mbar_init(bar_acc_empty + b, CL * kFfEpiWarps);
@@ -109,18 +127,32 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
   if (warp == kTmaWarp) {
     if (lane == 0) {
       uint32_t g = 0;
-      for (long long u = u_begin; u < units; u += u_step) {
+      long long cur_mp = -1;
+      int x_loads = 0;
+      for (long long u = u_begin; u < u_end; u += u_step) {
         const int nt = (int)(u % P.n_tiles);
-        const int m0 = ((int)(u / P.n_tiles) * CL + (int)rank) * 128, n0 = nt * 128;
+        const long long mp = u / P.n_tiles;
+        const int m0 = ((int)mp * CL + (int)rank) * 128, n0 = nt * 128;
+        if (XRES && mp != cur_mp) {   // new row pair: reload the resident x tile once its last MMAs have retired
+          if (x_loads > 0) mbar_wait(bar_x_free, (x_loads - 1) & 1);
+          if (rank == 0) mbar_arrive_expect_tx(bar_x_full, 2u * kblocks * kFfABytes);
+          for (int kb = 0; kb < kblocks; ++kb)
+            tma_load_2d_pair(smem + kb * kFfABytes, &P.tm_x, bar_x_full, kb * 64, m0, kEvictNormal);
+          cur_mp = mp;
+          ++x_loads;
+        }
         for (int kb = 0; kb < kblocks; ++kb, ++g) {
           const int s = g % NST;
           mbar_wait(bar_empty + s, ((g / NST) & 1) ^ 1);
-          uint8_t* a = smem + s * STAGE_BYTES;
+          uint8_t* a = ring + s * STAGE_BYTES;
           if (CL == 1) {
             mbar_arrive_expect_tx(bar_full + s, STAGE_BYTES);
             tma_load_2d(a, &P.tm_x, bar_full + s, kb * 64, m0, kEvictNormal);
             tma_load_2d(a + kFfABytes, &P.tm_w, bar_full + s, kb * 64, n0, kEvictLast);
             tma_load_2d(a + kFfABytes + kFfABytes, &P.tm_w, bar_full + s, kb * 64, P.N + n0, kEvictLast);
+          } else if (XRES) {
+            if (rank == 0) mbar_arrive_expect_tx(bar_full + s, 2 * STAGE_BYTES);
+            tma_load_2d_pair(a, &P.tm_w, bar_full + s, kb * 64, (int)rank * P.N + n0, kEvictLast);
           } else {
             // the leader's barrier collects the bytes of both CTAs' loads
             if (rank == 0) mbar_arrive_expect_tx(bar_full + s, 2 * STAGE_BYTES);
@@ -135,9 +167,17 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
       constexpr uint32_t idesc = make_idesc_bf16(CL == 2 ? 256 : 128, 256, 0, 0);
       const uint64_t desc0 = make_smem_desc_sw128(0, 16, 1024);
       uint32_t g = 0;
-      int i = 0;
-      for (long long u = u_begin; u < units; u += u_step, ++i) {
+      int i = 0, x_seen = 0;
+      long long cur_mp = -1;
+      for (long long u = u_begin; u < u_end; u += u_step, ++i) {
         const int b = i & 1;
+        const long long mp = u / P.n_tiles;
+        if (XRES && mp != cur_mp) {
+          mbar_wait(bar_x_full, x_seen & 1);
+          ++x_seen;
+          cur_mp = mp;
+        }
+        const bool last_of_x = XRES && (u + 1 >= u_end || (u + 1) / P.n_tiles != mp);
         mbar_wait(bar_acc_empty + b, ((i >> 1) & 1) ^ 1);   // the epilogue warps have drained this accumulator buffer
         tc_fence_after();
         for (int kb = 0; kb < kblocks; ++kb, ++g) {
@@ -145,8 +185,8 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
           mbar_wait(bar_full + s, (g / NST) & 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t aa = smem_u32(smem + s * STAGE_BYTES) >> 4;
-            const uint32_t ba = aa + (kFfABytes >> 4);
+            const uint32_t aa = smem_u32(XRES ? smem + kb * kFfABytes : ring + s * STAGE_BYTES) >> 4;
+            const uint32_t ba = XRES ? smem_u32(ring + s * STAGE_BYTES) >> 4 : aa + (kFfABytes >> 4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {   // 32 bytes per 16-column k-step inside the 128-byte swizzle row
               const uint64_t da = desc0 | (uint64_t)((aa + kk * 2) & 0x3FFF);
@@ -159,7 +199,10 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
               if (kb == kblocks - 1) tc_commit(bar_acc_full + b);
             } else {
               tc_commit_pair(bar_empty + s, (uint16_t)0b11);
-              if (kb == kblocks - 1) tc_commit_pair(bar_acc_full + b, (uint16_t)0b11);
+              if (kb == kblocks - 1) {
+                tc_commit_pair(bar_acc_full + b, (uint16_t)0b11);
+                if (last_of_x) tc_commit_pair(bar_x_free, (uint16_t)0b11);
+              }
             }
           }
           __syncwarp();
@@ -172,7 +215,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     int i = 0;
-    for (long long u = u_begin; u < units; u += u_step, ++i) {
+    for (long long u = u_begin; u < u_end; u += u_step, ++i) {
       const int b = i & 1;
       const int nt = (int)(u % P.n_tiles);
       const long long row = ((u / P.n_tiles) * CL + rank) * 128 + quarter * 32 + lane;
