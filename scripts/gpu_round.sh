@@ -15,5 +15,5 @@ tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.log; tail -3 gpurun_out/
 else
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ip_xattn -s 2 -c 1 -o gpurun_out/prof_ip -f python scripts/perf_ip_one.py > gpurun_out/ncu_ip.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ff_geglu -s 2 -c 1 -o gpurun_out/prof_ff -f python scripts/perf_ff_one.py > gpurun_out/ncu_ff.log 2>&1
-tail -2 gpurun_out/ncu_ip.log gpurun_out/ncu_ff.log
+tail -n 2 gpurun_out/ncu_ip.log; tail -n 2 gpurun_out/ncu_ff.log
 fi
