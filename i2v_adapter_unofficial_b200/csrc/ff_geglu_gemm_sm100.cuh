@@ -230,26 +230,34 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
       mbar_wait(bar_acc_full + b, (i >> 1) & 1);
       tc_fence_after();
       const uint32_t tm = tmem_base + lane_addr + b * 256 + half * CW;
+      const int trow = quarter * 32 + lane;                     // row of the tile
+      uint8_t* srow = sm_out + (half * CW / 64) * kFfABytes + trow * 128;   // this row in its 64-column half
+      const int c16 = (half * CW % 64) / 8;                     // first 16-byte chunk of this warp's columns in the row
+      // The warp's whole share of the accumulator (32 hidden + 32 gate columns) goes to registers first and the buffer is
+      // handed back to the MMA warp at once: a TMEM buffer is then busy for a tile's MMAs plus one load, not for the
+      // whole epilogue, which matters where a tile's MMAs are shorter than its epilogue (K = 320).
+      static_assert(NCH == 2, "register budget: two 16-column chunks per warp");
+      uint32_t h[NCH][16], gt[NCH][16];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        tmem_ld_x16(tm + ch * 16, h[ch]);
+        tmem_ld_x16(tm + 128 + ch * 16, gt[ch]);
+      }
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(bar_acc_empty + b);
+        else mbar_arrive_cluster(bar_acc_empty + b, 0u);   // the leader's barrier
+      }
       // the staging tile is free once the previous tile's stores have read it (the issuing thread waits, then everyone
       // passes this barrier)
       if (threadIdx.x == 0 && i > 0) tma_store_wait_read();
       named_bar_sync(1, kFfEpiWarps * 32);
-      const int trow = quarter * 32 + lane;                     // row of the tile
-      uint8_t* srow = sm_out + (half * CW / 64) * kFfABytes + trow * 128;   // this row in its 64-column half
-      const int c16 = (half * CW % 64) / 8;                     // first 16-byte chunk of this warp's columns in the row
-      // chunks of 16 columns, software-pipelined: the TMEM loads of chunk ch + 1 are in flight under the GELUs of ch
-      uint32_t h[2][16], gt[2][16];
-      tmem_ld_x16(tm, h[0]);
-      tmem_ld_x16(tm + 128, gt[0]);
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        tc_wait_ld();
-        if (ch + 1 < NCH) {
-          tmem_ld_x16(tm + (ch + 1) * 16, h[(ch + 1) & 1]);
-          tmem_ld_x16(tm + 128 + (ch + 1) * 16, gt[(ch + 1) & 1]);
-        }
-        const uint32_t* hc = h[ch & 1];
-        const uint32_t* gc = gt[ch & 1];
+        const uint32_t* hc = h[ch];
+        const uint32_t* gc = gt[ch];
         const uint64_t* bh2 = reinterpret_cast<const uint64_t*>(wb + ch * 16);
         const uint64_t* bg2 = reinterpret_cast<const uint64_t*>(wb + 32 + ch * 16);
         uint32_t o[8];
@@ -267,12 +275,6 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
       }
       if (P.ld > P.N && nt == 0 && half == 0 && row < P.rows)   // ones column for the next GEMM's deferred bias
         *reinterpret_cast<uint4*>(P.out + row * P.ld + P.N) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CL == 1) mbar_arrive(bar_acc_empty + b);
-        else mbar_arrive_cluster(bar_acc_empty + b, 0u);   // the leader's barrier
-      }
       fence_proxy_async_smem();                   // generic-proxy writes of the staging tile -> the store's async proxy
       named_bar_sync(2, kFfEpiWarps * 32);
       if (threadIdx.x == 0) {                     // rows past the end of y are clipped by the tensor map
