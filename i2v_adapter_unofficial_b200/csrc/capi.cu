@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/i2v_attn_b200.h"
 #include "dense_attn_sm100.cuh"
@@ -948,10 +949,15 @@ int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, cons
   P.x2 = (const __nv_bfloat16*)x2; P.C1 = x2 ? C1 : C;
   P.w = (const __nv_bfloat16*)w; P.b = (const __nv_bfloat16*)b;
   P.N = N; P.S = S; P.C = C; P.G = G; P.fg = fg; P.eps = eps; P.silu = silu; P.perm = perm;
-  int ch = (4 * di->sms + N - 1) / N;   // ~4 CTAs per SM in total
-  if (ch > kGnMaxChunks) ch = kGnMaxChunks;
-  if (ch > (S + 7) / 8) ch = (S + 7) / 8;
-  if (ch < 1) ch = 1;
+  // row chunks per image: one full wave of CTAs and no second, partial one (statistics: four 256-thread CTAs per SM;
+  // apply: two CTAs of up to 512 threads per SM) -- rounding the count up cost a whole extra wave for 16 CTAs
+  auto chunks = [&](int ctas_per_sm) {
+    int ch = ctas_per_sm * di->sms / N;
+    if (ch > kGnMaxChunks) ch = kGnMaxChunks;
+    if (ch > (S + 7) / 8) ch = (S + 7) / 8;
+    return ch < 1 ? 1 : ch;
+  };
+  const int ch = chunks(4);
   P.rows_per_chunk = (S + ch - 1) / ch;
   P.CH = (S + P.rows_per_chunk - 1) / P.rows_per_chunk;
   P.partial = scratch;
@@ -967,7 +973,11 @@ int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, cons
   // thread = (channel vector, row phase): as many row phases as fit 512 threads
   const int rpp = VC >= 512 ? 1 : 512 / VC;
   const int ablock = (VC * rpp + 31) / 32 * 32;
-  i2v::gn_apply_rows_kernel<<<grid, ablock, 0, (cudaStream_t)stream>>>(P);
+  i2v::GnNhwcParams PA = P;
+  const int cha = chunks(2);
+  PA.rows_per_chunk = (S + cha - 1) / cha;
+  dim3 agrid((S + PA.rows_per_chunk - 1) / PA.rows_per_chunk, N);
+  i2v::gn_apply_rows_kernel<<<agrid, ablock, 0, (cudaStream_t)stream>>>(PA);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(3);
   return 0;

@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnNhwcParams P) 
 
 // Thread = (channel vector, row phase): the thread's eight channels keep their (A, B, T) coefficients in registers
 // (y = (x + T) * A + B), so the row loop is loads, eight FMAs and a store per 16-byte vector; block = C/8 * rows-per-pass.
-__global__ void __launch_bounds__(512) gn_apply_rows_kernel(const GnNhwcParams P) {
+__global__ void __launch_bounds__(512, 2) gn_apply_rows_kernel(const GnNhwcParams P) {
   const int chunk = blockIdx.x, n = blockIdx.y;
   const int v = n / P.fg, f = n - v * P.fg;
   const int VC = P.C / 8;
