@@ -331,7 +331,9 @@ def test_adapter_checkpoints_loaded_after_install_take_effect(tmp_path):
 
 # ---- feed-forward input projection fused with GEGLU (tcgen05 GEMM) ------------------------------------------------
 @pytest.mark.parametrize("case", [(256, 320, 1280, True), (1000, 64, 128, False), (384, 640, 2560, True),
-                                  (130, 1280, 5120, True), (5000, 320, 1280, False)],
+                                  (130, 1280, 5120, True), (5000, 320, 1280, False),
+                                  (100, 320, 1280, True),       # one row block: the single-CTA kernel
+                                  (2048 + 77, 256, 384, True)],  # odd number of row blocks, three n-tiles
                          ids=lambda c: "rows{}K{}N{}bias{}".format(*c))
 @pytest.mark.parametrize("ones", [False, True])
 def test_ff_geglu_gemm_matches_fp32_reference(case, ones):
