@@ -407,7 +407,9 @@ def test_group_norm_nhwc_two_sources_equals_concatenation(case, silu):
     ref = ops.group_norm_nhwc(cat, w, bias, G, 1e-5, 1, silu=silu)
     out = ops.group_norm_nhwc(a, w, bias, G, 1e-5, 1, silu=silu, x2=b)
     assert ops.is_channels_last(out) and out.shape == ref.shape
-    assert (out.float() - ref.float()).abs().max().item() <= 2e-2   # channel sums accumulate in a different order
+    # channel sums accumulate in a different order: at most one bf16 ulp apart (0.031 for |y| in [4, 8))
+    err = (out.float() - ref.float()).abs()
+    assert (err <= 2e-2 * torch.clamp(ref.float().abs() / 2, min=1.0)).all(), err.max().item()
 
 
 def test_up_block_without_concatenation_matches_module():
