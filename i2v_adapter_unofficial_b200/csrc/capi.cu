@@ -560,6 +560,10 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
         if (cfgsel == 1) return launch_ip_stream<40, 8, 2, 3, 1>(P, di->sms, (cudaStream_t)stream);
         if (cfgsel == 2) return launch_ip_stream<40, 4, 1, 3, 2>(P, di->sms, (cudaStream_t)stream);
         // the pipeline's token counts (77 text + 4 image) get the instantiation with compile-time key classes
+        // four heads per unit, two CTAs per SM at 94 registers: no spills (the two-head, three-CTA configuration is held
+        // to 72 registers and spills in the softmax): 102 us against 115 us at C2 level 0; cfgsel 3 = the latter
+        if (std77 && cfgsel == 3) return launch_ip_stream<40, 2, 1, 3, 3, 77, 81>(P, di->sms, (cudaStream_t)stream);
+        if (std77 && heads % 4 == 0) return launch_ip_stream<40, 4, 1, 3, 2, 77, 81>(P, di->sms, (cudaStream_t)stream);
         if (std77) return launch_ip_stream<40, 2, 1, 3, 3, 77, 81>(P, di->sms, (cudaStream_t)stream);
         return launch_ip_stream<40, 2, 1, 3, 3>(P, di->sms, (cudaStream_t)stream);   // 3 CTAs per SM
       }

@@ -17,7 +17,7 @@ for (B, S, d) in [(32, 4096, 40), (32, 1024, 80), (32, 256, 160), (32, 64, 160)]
     k, v = kv[:, :, 0], kv[:, :, 1]
     nbytes = 2 * q.numel() * 2
     res = {}
-    for name, key, cfg in (("stream", 0, 0), ("stream-rt", 2, 0), ("stream-1", 0, 1), ("stream-2", 0, 2), ("tcgen05", 1, 0)):
+    for name, key, cfg in (("stream", 0, 0), ("stream-rt", 2, 0), ("stream-3", 0, 3), ("tcgen05", 1, 0)):
         lib.i2v_set_tuning(5, key)
         lib.i2v_set_tuning(6, cfg)
         for _ in range(3):

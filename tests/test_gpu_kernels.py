@@ -175,7 +175,7 @@ def test_kv_group_indexing_is_bit_identical_to_the_repeated_tensor():
 
 @pytest.mark.parametrize("case", [(4, 8, 256, 40, 2, 77, 4), (2, 8, 1024, 80, 1, 77, 4), (2, 8, 64, 160, 2, 50, 14),
                                   (2, 8, 300, 40, 1, 77, 16), (2, 2, 128, 64, 1, 10, 1), (4, 8, 272, 160, 4, 77, 4),
-                                  (2, 8, 1000, 40, 2, 77, 4)],
+                                  (2, 8, 1000, 40, 2, 77, 4), (2, 6, 200, 40, 1, 77, 4)],
                          ids=lambda c: "B{}H{}S{}d{}g{}n{}+{}".format(*c))
 @pytest.mark.parametrize("mode", ["fast", "generic"])
 def test_ip_adapter_decoupled_cross_attention_matches_oracle(case, mode):
