@@ -10,22 +10,25 @@
 // is written.
 //
 // Persistent, warp-specialised: 1 TMA warp (x tile 128 x 64 and two 128 x 64 weight boxes -- hidden rows n0.. and gate
-// rows N + n0.. of the same nn.Linear weight, stacked into one 256-row K-major operand -- through a 4-stage ring), 1
+// rows N + n0.. of the same nn.Linear weight, stacked into one 256-row K-major operand -- through a 3-stage ring), 1
 // MMA-issuing warp (tcgen05.mma M = 128, N = 256, K = 16; fp32 accumulators double-buffered in TMEM: 2 x 256
 // columns), 16 epilogue warps (lane quarter x column group) that overlap tile i's GELU with tile i+1's MMAs.
 // Tiles are walked n-fastest, so the CTAs running at the same time share x row blocks through L2.
+// Epilogue: the warp's share of the accumulator goes to registers and the TMEM buffer is released at once; biases from a
+// per-warp fp32 table in shared memory; MUFU-free GELU on packed fp32 pairs (geglu_pair_poly); the bf16 tile is staged
+// in 128-byte-swizzled shared memory and written with two tiled TMA stores.
 //
 // CL = 2: CTA pairs (clusters of two on one TPC) run the 2-SM MMA, tcgen05 cta_group::2, M = 256: the two CTAs own two
 // row blocks of the same n-tile, each loads its own x tile and HALF of the weight operand (CTA 0 the hidden box, CTA 1
 // the gate box) into its own shared memory, the leader CTA issues the MMAs for both and each CTA's TMEM receives its
 // 128 rows of the 256 x 256 accumulator.  Per k-block a CTA takes in and reads back 32 KB instead of 48 KB: the
 // single-CTA kernel is bound by exactly that (shared-memory bandwidth: 12 KB read + 12 KB written per k-step = 192 clk
-// against 128 clk of math; at K = 320 the L2 -> SM path), and the stages become small enough for a 6-deep ring.
+// against 128 clk of math; at K = 320 the L2 -> SM path), and the stages become small enough for a 5-deep ring next to
+// the output staging tile.
 // Barriers: full[s] lives in the leader and counts both CTAs' TMA bytes; empty[s] / acc_full[b] exist in both CTAs and
 // get the leader's multicast commits; acc_empty[b] lives in the leader and takes both CTAs' epilogue warps.
 //
-// XRES (CL = 2, K <= 320: SD1.5 level 0, where a tile is only five k-blocks and the kernel is bound by TMA latency
-// against the bytes a CTA can keep in flight): every pair owns a contiguous range of the (row pair, n-tile) order, so
+// XRES (CL = 2, K <= 320: SD1.5 level 0, where a tile is only five k-blocks): every pair owns a contiguous range of the (row pair, n-tile) order, so
 // consecutive units share their x rows; the CTA's whole 128 x K x tile stays resident (80 KB) and only its half of the
 // weight tile streams through the ring -- half the bytes per tile.
 #pragma once
