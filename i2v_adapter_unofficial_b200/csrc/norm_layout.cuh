@@ -249,30 +249,9 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
   return fmaf(-(ag * e), q * t, fmaxf(g, 0.f));
 }
 
-// Two of them at once on packed fp32 pairs (FFMA2 / FMUL2 take one issue slot for both lanes): h * gelu(g) for a pair.
-__device__ __forceinline__ uint64_t geglu_pair(uint64_t h2, uint64_t g2) {
-  float g0, g1;
-  f2_unpack(g2, g0, g1);
-  const float a0 = fabsf(g0), a1 = fabsf(g1);
-  const uint64_t ag2 = f2_pack(a0, a1);
-  float d0, d1, x0, x1;
-  f2_unpack(f2_fma(ag2, f2_pack(0.23164189f, 0.23164189f), f2_pack(1.f, 1.f)), d0, d1);
-  f2_unpack(f2_mul(f2_mul(g2, g2), f2_pack(-0.72134752f, -0.72134752f)), x0, x1);
-  const uint64_t t2 = f2_pack(rcp_approx(d0), rcp_approx(d1));
-  const uint64_t e2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
-  uint64_t q = f2_fma(t2, f2_pack(0.5307027145f, 0.5307027145f), f2_pack(-0.7265760135f, -0.7265760135f));
-  q = f2_fma(q, t2, f2_pack(0.7107068705f, 0.7107068705f));
-  q = f2_fma(q, t2, f2_pack(-0.142248368f, -0.142248368f));
-  q = f2_fma(q, t2, f2_pack(0.127414796f, 0.127414796f));
-  const uint64_t relu2 = f2_pack(fmaxf(g0, 0.f), fmaxf(g1, 0.f));
-  // gelu = relu(g) - (|g| e) (q t)
-  const uint64_t neg = f2_mul(f2_mul(ag2, e2), f2_mul(q, t2));
-  return f2_mul(h2, f2_sub(relu2, neg));
-}
-
-// MUFU-free variant for the fused feed-forward epilogue, which is bound by pipe time, not by HBM: the two MUFU ops per
-// value above cost 16 XU clocks per warp-value on top of the FMA-pipe work and the in-order warps do not overlap the
-// two pipes well.  gelu(g) = relu(g) - r(|g|) with r(a) = a * erfc(a / sqrt 2) / 2, a smooth bump in [0, 0.17] that is
+// h * gelu(g) for a packed fp32 pair, MUFU-free, for the fused feed-forward epilogue, which is bound by pipe time and not
+// by HBM: the two MUFU ops per value of gelu_erf_fast cost 16 XU clocks per warp-value on top of the FMA-pipe work and
+// the in-order warps do not overlap the two pipes well.  gelu(g) = relu(g) - r(|g|) with r(a) = a * erfc(a / sqrt 2) / 2, a smooth bump in [0, 0.17] that is
 // below 1.5e-6 beyond a = 5: a degree-12 polynomial in t = 2 min(a, 5) / 5 - 1 (Chebyshev interpolant, monomial form;
 // max |error| 8.1e-6 in fp32 Horner arithmetic against erf-GELU in fp64, i.e. 1/60 of a bf16 ulp at 0.1).
 __device__ __forceinline__ uint64_t geglu_pair_poly(uint64_t h2, uint64_t g2) {

@@ -99,14 +99,6 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity,
 // ----------------------------------------------------------------------------------------------
 // Proxy fences
 // ----------------------------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-}
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -148,18 +140,6 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// Multicast flavour: the box lands at the same shared-memory offset of every CTA in `cta_mask` and completes bytes on the
-// mbarrier at the same offset of each of them.
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
-                                                      uint16_t cta_mask, uint64_t cache_hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5, %6;"
-      :
-      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-        "h"(cta_mask), "l"(cache_hint)
-      : "memory");
-}
 // CTA-pair flavour (tcgen05 cta_group::2): executed by both CTAs of the pair, the bytes are counted on the mbarrier of
 // the pair's leader (CTA 0): clearing the peer bit of the shared::cluster address selects it.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
@@ -234,16 +214,6 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-
-// The same arrival delivered to the mbarrier at this offset in every CTA of `cta_mask` (a stage shared through multicast
-// loads is free only when every CTA that received it has consumed it).
-__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
 }
 
 // CTA pair: all MMAs issued so far by this thread for the pair; one arrival on the mbarrier at this offset in every CTA
