@@ -556,10 +556,13 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnNhwcParams P) 
   const int v = i / P.G, g = i - v * P.G;
   float a = 0.f, b = 0.f;
   const int n_part = P.fg * P.CH;
+  // the fg * CH partials of this (video, group) are rows (v * fg + f, ch) of [N, CH, G, 2]: consecutive j = f * CH + ch
+  // are consecutive rows, so the address is affine in j; four independent loads in flight per lane
+  const float2* base = reinterpret_cast<const float2*>(P.partial) + ((long long)v * P.fg * P.CH) * P.G + g;
+#pragma unroll 4
   for (int j = lane; j < n_part; j += 32) {
-    const int f = j / P.CH, ch = j - f * P.CH;
-    const float* pp = P.partial + ((((long long)v * P.fg + f) * P.CH + ch) * P.G + g) * 2;
-    a += pp[0]; b += pp[1];
+    const float2 p = base[(long long)j * P.G];
+    a += p.x; b += p.y;
   }
   a = warp_sum(a);
   b = warp_sum(b);
