@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = (
     "i2v_reshard_pack",
     "i2v_reshard_unpack",
     "i2v_set_tuning",
+    "i2v_prof_arm",
+    "i2v_prof_read",
     "i2v_layernorm_fwd",
     "i2v_layernorm_pre_fwd",
     "i2v_geglu_ld_fwd",
@@ -99,6 +101,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_set_tuning.restype = i
     lib.i2v_set_tuning.argtypes = [i, i]
     ll = ctypes.c_longlong
+    lib.i2v_prof_arm.restype = i
+    lib.i2v_prof_arm.argtypes = [i, ll, ll, i]
+    lib.i2v_prof_read.restype = i
+    lib.i2v_prof_read.argtypes = [i, ctypes.POINTER(ctypes.c_float), i]
     lib.i2v_layernorm_fwd.restype = i
     lib.i2v_layernorm_fwd.argtypes = [p, p, p, p, p, ll, i, i, f, p]
     lib.i2v_geglu_fwd.restype = i
@@ -152,3 +158,20 @@ def check(code: int) -> None:
 
 def launch_count() -> int:
     return int(load().i2v_launch_count())
+
+
+PROF_DENSE, PROF_TEMPORAL, PROF_IP, PROF_GEMM = 1, 2, 3, 4
+
+
+def prof_arm(kind: int, match_a: int = 0, match_b: int = 0, max_pairs: int = 64) -> None:
+    """Bracket the next ``max_pairs`` matching launches of a kernel class with CUDA events (``i2v_prof_arm``)."""
+    check(load().i2v_prof_arm(kind, match_a, match_b, max_pairs))
+
+
+def prof_read(kind: int, capacity: int = 256):
+    """Durations (ms) of the recorded pairs; synchronise first."""
+    buf = (ctypes.c_float * capacity)()
+    n = load().i2v_prof_read(kind, buf, capacity)
+    if n < 0:
+        check(n)
+    return [float(buf[i]) for i in range(n)]

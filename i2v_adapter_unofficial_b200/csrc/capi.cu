@@ -28,6 +28,49 @@ unsigned long long* g_trace = nullptr;
 int g_trace_cta = 0;
 #endif
 
+int fail(int code, const char* fmt, ...);
+
+// ---------------------------------------------------------------------------------------------------------
+// Launch timing (i2v_prof_*): CUDA-event pairs recorded by the library immediately around the kernel launch, after
+// the host-side tensor-map encoding, on the launching stream.  While the stream is being captured into a CUDA graph
+// the records become external event-record nodes, so every replay of the graph re-records them and the caller reads
+// the durations of the kernels *inside the replayed step* after synchronising.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kProfKinds = 6;        // 1 dense fused (level-0 class), 2 temporal, 3 IP-Adapter, 4 feed-forward GEMM, 5 token GEMM
+constexpr int kProfMaxPairs = 256;
+struct ProfKind {
+  bool armed = false;
+  long long match_a = 0, match_b = 0;   // 0 = any
+  int cap = 0, used = 0;
+  cudaEvent_t e0[kProfMaxPairs], e1[kProfMaxPairs];
+  int created = 0;
+};
+ProfKind g_prof[kProfKinds];
+
+void prof_record(cudaEvent_t ev, cudaStream_t stream) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cs);
+  if (cs == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(ev, stream, cudaEventRecordExternal);
+  else cudaEventRecord(ev, stream);
+}
+
+struct ProfScope {
+  ProfKind* k = nullptr;
+  int slot = -1;
+  cudaStream_t stream;
+  ProfScope(int kind, long long a, long long b, cudaStream_t st) : stream(st) {
+    ProfKind& pk = g_prof[kind];
+    if (!pk.armed || pk.used >= pk.cap) return;
+    if ((pk.match_a && pk.match_a != a) || (pk.match_b && pk.match_b != b)) return;
+    k = &pk;
+    slot = pk.used++;
+    prof_record(pk.e0[slot], stream);
+  }
+  ~ProfScope() {
+    if (k) prof_record(k->e1[slot], stream);
+  }
+};
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -193,6 +236,7 @@ int launch_ip_stream(const i2v::IpStreamParams& P, int sms, cudaStream_t stream)
   }
   const long long units = (long long)P.batch * (P.heads / HG) * ((P.sq + Cfg::ROWS - 1) / Cfg::ROWS);
   const long long grid = units < (long long)sms * MINB ? units : (long long)sms * MINB;
+  ProfScope prof(3, P.sq, P.batch, stream);
   kern<<<(unsigned)grid, i2v::kIpThreads, Cfg::SMEM_BYTES, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -239,6 +283,7 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
   }
   // g_tuning[2]: exp2-emulation split override for experiments (pairs out of 8 on the FMA pipe); 0 = default
   const int emu = g_tuning[2] > 0 ? g_tuning[2] - 1 : -1;
+  ProfScope prof(seg_split >= 0 ? 3 : 1, sq, batch, stream);
   switch (dk) {
     case 16:  return launch_dense_cfg<i2v::DenseCfg<16, 128, 4>>(P, stream);
     case 32:  return launch_dense_cfg<i2v::DenseCfg<32, 128, 4>>(P, stream);
@@ -361,6 +406,7 @@ int launch_temporal_cfg(const i2v::TemporalParams& P, int sms, cudaStream_t stre
   const long long units = (long long)P.n_pos * (P.heads / HG);
   long long grid = (long long)sms * per_sm;
   if (grid > units) grid = units;
+  ProfScope prof(2, P.n_pos, D, stream);
   kern<<<(unsigned)grid, i2v::kTemporalThreads, smem, stream>>>(P, stages);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -422,6 +468,42 @@ int i2v_set_tuning(int key, int value) {
   if (key < 0 || key >= 8) return fail(I2V_ERR_BAD_SHAPE, "unknown tuning key %d", key);
   g_tuning[key] = value;
   return 0;
+}
+
+int i2v_prof_arm(int kind, long long match_a, long long match_b, int max_pairs) {
+  if (kind <= 0 || kind >= kProfKinds) return fail(I2V_ERR_BAD_SHAPE, "i2v_prof_arm: unknown kernel class %d", kind);
+  ProfKind& pk = g_prof[kind];
+  if (max_pairs <= 0) {   // disarm: launches stop taking new pairs; pairs already recorded (or captured) stay readable
+    pk.armed = false;
+    return 0;
+  }
+  if (max_pairs > kProfMaxPairs) max_pairs = kProfMaxPairs;
+  while (pk.created < max_pairs) {
+    CUDA_TRY(cudaEventCreate(&pk.e0[pk.created]));
+    CUDA_TRY(cudaEventCreate(&pk.e1[pk.created]));
+    ++pk.created;
+  }
+  pk.armed = true;
+  pk.match_a = match_a;
+  pk.match_b = match_b;
+  pk.cap = max_pairs;
+  pk.used = 0;
+  return 0;
+}
+
+int i2v_prof_read(int kind, float* ms_out, int capacity) {
+  if (kind <= 0 || kind >= kProfKinds) return fail(I2V_ERR_BAD_SHAPE, "i2v_prof_read: unknown kernel class %d", kind);
+  ProfKind& pk = g_prof[kind];
+  int n = 0;
+  for (; n < pk.used && n < capacity; ++n) {
+    cudaError_t e = cudaEventElapsedTime(&ms_out[n], pk.e0[n], pk.e1[n]);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(I2V_ERR_CUDA, "i2v_prof_read: pair %d not complete (%s): synchronise the stream first", n,
+                  cudaGetErrorString(e));
+    }
+  }
+  return n;
 }
 
 int i2v_sdpa_fwd(const i2v_tensor* q, const i2v_tensor* k, const i2v_tensor* v, const i2v_tensor* o, int batch,
@@ -504,6 +586,7 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
     P.prob[i].kv_group = s.kv_group;
   }
   const int emu = g_tuning[2] > 0 ? g_tuning[2] - 1 : -1;
+  ProfScope prof(1, seq, batch, (cudaStream_t)stream);
   switch (emu) {
     case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, true>>(P, (cudaStream_t)stream);
     case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true>>(P, (cudaStream_t)stream);

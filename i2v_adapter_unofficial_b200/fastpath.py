@@ -35,15 +35,40 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+from .processors import _CACHE_EPOCH
+
+
+#: how often each swapped forward handed the call back to the module's original (stock PyTorch) forward because a
+#: precondition failed -- `bench.py` asserts this stays empty for the measured configuration
+FALLBACKS: Dict[str, int] = {}
+
+
+def _fallback(kind: str, original: Callable, *args, **kwargs):
+    FALLBACKS[kind] = FALLBACKS.get(kind, 0) + 1
+    return original(*args, **kwargs)
+
+
+def fallback_counts() -> Dict[str, int]:
+    return dict(FALLBACKS)
+
+
+def reset_fallback_counts() -> None:
+    FALLBACKS.clear()
 
 
 def _fast_ok(x: torch.Tensor, module: nn.Module) -> bool:
     return x.is_cuda and x.dtype == torch.bfloat16 and not module.training and not torch.is_grad_enabled()
 
 
+def _norm_dtype_ok(norm: nn.Module, x: torch.Tensor) -> bool:
+    """The norm kernels read bf16 parameters (autocast setups keep them in fp32: those go to the stock forward)."""
+    w = getattr(norm, "weight", None)
+    return w is None or w.dtype == x.dtype
+
+
 def _ln(x: torch.Tensor, norm: nn.LayerNorm, pe: Optional[torch.Tensor] = None,
         pre: Optional[torch.Tensor] = None) -> torch.Tensor:
-    if norm.weight is None or norm.bias is None:
+    if norm.weight is None or norm.bias is None or norm.weight.dtype != x.dtype:
         if pre is not None:
             x = x + pre
         y = F.layer_norm(x, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
@@ -88,14 +113,15 @@ class _Deferred:
         return None if t is None else (t.data_ptr(), t._version)
 
     def get1(self, b1, like: torch.Tensor):
-        key = (self._sig(b1), like.dtype, like.device)
+        key = (_CACHE_EPOCH[0], self._sig(b1), like.dtype, like.device)
         if key != getattr(self, "key1", None):
             self.val1 = b1.to(like.dtype).contiguous()
             self.key1 = key
         return self.val1
 
     def get(self, b1, b2, ff_out: nn.Linear, like: torch.Tensor):
-        key = (self._sig(b1), self._sig(b2), self._sig(ff_out.weight), self._sig(ff_out.bias), like.dtype, like.device)
+        key = (_CACHE_EPOCH[0], self._sig(b1), self._sig(b2), self._sig(ff_out.weight), self._sig(ff_out.bias),
+               like.dtype, like.device)
         if key != self.key:
             C = ff_out.weight.shape[0]
             zero = torch.zeros(C, dtype=torch.float32, device=like.device)
@@ -124,7 +150,7 @@ class _PE:
 
     def get(self, pos_embed: nn.Module, frames: int, like: torch.Tensor) -> torch.Tensor:
         pe = pos_embed.pe
-        key = (pe.data_ptr(), pe._version, frames, like.device, like.dtype)
+        key = (_CACHE_EPOCH[0], pe.data_ptr(), pe._version, frames, like.device, like.dtype)
         if key != self.key:
             self.val = pe[0, :frames].to(device=like.device, dtype=like.dtype).contiguous()
             self.key = key
@@ -232,7 +258,7 @@ def _make_block_forward(module: nn.Module, original: Callable, is_i2v: bool):
                   and isinstance(module.norm1, nn.LayerNorm) and isinstance(module.norm3, nn.LayerNorm)
                   and _is_geglu_ff(module.ff) and getattr(module, "_chunk_size", None) is None)
         if not simple:
-            return original(hidden_states, *args, **kwargs)
+            return _fallback("transformer_block", original, hidden_states, *args, **kwargs)
         kw = dict(bound.get("cross_attention_kwargs") or {})
         kw.pop("gligen", None)
         return _block_forward_fast(module, hidden_states, bound.get("encoder_hidden_states"),
@@ -251,7 +277,8 @@ def _layout_ok(x: torch.Tensor, norm: nn.GroupNorm) -> bool:
         return False
     _, C, h, w = x.shape
     G = norm.num_groups
-    return C % 64 == 0 and (h * w) % 8 == 0 and C % G == 0 and (C // G) % 2 == 0 and x.shape[0] <= 65535
+    return (C % 64 == 0 and (h * w) % 8 == 0 and C % G == 0 and (C // G) % 2 == 0 and x.shape[0] <= 65535
+            and _norm_dtype_ok(norm, x))
 
 
 def _nhwc_ok(x: torch.Tensor, norm: nn.GroupNorm) -> bool:
@@ -259,7 +286,8 @@ def _nhwc_ok(x: torch.Tensor, norm: nn.GroupNorm) -> bool:
     if not (ops.is_channels_last(x) and isinstance(norm, nn.GroupNorm) and norm.affine):
         return False
     C, G = x.shape[1], norm.num_groups
-    return C % 8 == 0 and C % G == 0 and C <= 4096 and x.shape[0] <= 65535 and not x.is_contiguous()
+    return (C % 8 == 0 and C % G == 0 and C <= 4096 and x.shape[0] <= 65535 and not x.is_contiguous()
+            and _norm_dtype_ok(norm, x))
 
 
 def _make_transformer2d_forward(module: nn.Module, original: Callable):
@@ -280,7 +308,7 @@ def _make_transformer2d_forward(module: nn.Module, original: Callable):
                 and len(args) <= len(names) and set(kwargs) <= set(names) and (conv_proj or lin_proj)
                 and module.proj_out.weight.shape[0] == hidden_states.shape[1])
         if not simple and not nhwc:
-            return original(hidden_states, *args, **kwargs)
+            return _fallback("transformer_2d", original, hidden_states, *args, **kwargs)
         N, C, h, w = hidden_states.shape
         norm = module.norm
         # :218-234  GroupNorm(32, eps 1e-6) -> proj_in -> (BF, S, inner), without the NCHW intermediate
@@ -324,9 +352,9 @@ def _make_temporal_forward(module: nn.Module, original: Callable):
         nhwc = (_fast_ok(hidden_states, module) and _nhwc_ok(hidden_states, module.norm)
                 and hidden_states.shape[0] % max(num_frames, 1) == 0 and isinstance(module.proj_in, nn.Linear))
         if not simple and not nhwc:
-            return original(hidden_states, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
-                            class_labels=class_labels, num_frames=num_frames,
-                            cross_attention_kwargs=cross_attention_kwargs, return_dict=return_dict)
+            return _fallback("temporal_model", original, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                             timestep=timestep, class_labels=class_labels, num_frames=num_frames,
+                             cross_attention_kwargs=cross_attention_kwargs, return_dict=return_dict)
         norm = module.norm
         # GroupNorm over (C/G, F, h, w) per video, then (BF, C, h, w) -> (B*S, F, C) in the same pass
         if nhwc:
@@ -362,7 +390,7 @@ def _is_silu(fn) -> bool:
 def _resnet_simple(module: nn.Module, x: torch.Tensor, temb) -> bool:
     """The ResnetBlock2D configurations the channels-last forward below covers (everything SD1.5 uses)."""
     return (_fast_ok(x, module) and temb is not None and _nhwc_ok(x, module.norm1)
-            and isinstance(module.norm2, nn.GroupNorm) and module.norm2.affine
+            and isinstance(module.norm2, nn.GroupNorm) and module.norm2.affine and _norm_dtype_ok(module.norm2, x)
             and _is_silu(getattr(module, "nonlinearity", None))
             and getattr(module, "time_emb_proj", None) is not None
             and getattr(module, "time_embedding_norm", "default") in (None, "default")
@@ -436,7 +464,7 @@ def _make_resnet_forward(module: nn.Module, original: Callable):
     @functools.wraps(original)
     def forward(x, temb=None, *args, **kwargs):
         if not _resnet_simple(module, x, temb):
-            return original(x, temb, *args, **kwargs)
+            return _fallback("resnet", original, x, temb, *args, **kwargs)
         return _resnet_forward_nhwc(module, x, temb)
 
     return forward
@@ -451,8 +479,12 @@ def _make_upblock_forward(module: nn.Module, original: Callable, cross: bool):
         names = (("enable_cross_frame_attn", "encoder_hidden_states", "cross_attention_kwargs", "upsample_size",
                   "attention_mask", "encoder_attention_mask", "num_frames") if cross
                  else ("upsample_size", "scale", "num_frames"))
-        if len(args) > len(names) or not set(kwargs) <= set(names):
-            return original(hidden_states, res_hidden_states_tuple, temb, *args, **kwargs)
+        # FreeU (enable_freeu sets s1/s2/b1/b2 on the up blocks) rescales hidden / skip before the concatenation and
+        # training / gradient checkpointing need the stock loop: those calls keep the original forward
+        freeu = all(getattr(module, a, None) for a in ("s1", "s2", "b1", "b2"))
+        if (len(args) > len(names) or not set(kwargs) <= set(names) or not _fast_ok(hidden_states, module) or freeu
+                or getattr(module, "gradient_checkpointing", False) and module.training):
+            return _fallback("up_block", original, hidden_states, res_hidden_states_tuple, temb, *args, **kwargs)
         kw = dict(zip(names, args))
         kw.update(kwargs)
         num_frames = kw.get("num_frames", 1)
@@ -464,6 +496,7 @@ def _make_upblock_forward(module: nn.Module, original: Callable, cross: bool):
             if "forward" in resnet.__dict__ and _pair_ok(resnet, hidden_states, res, temb):
                 hidden_states = _resnet_forward_nhwc(resnet, hidden_states, temb, res)
             else:
+                FALLBACKS["up_block_concat"] = FALLBACKS.get("up_block_concat", 0) + 1
                 hidden_states = resnet(torch.cat([hidden_states, res], dim=1), temb)
             if attn is not None:
                 hidden_states = attn(hidden_states, enable_cross_frame_attn=kw.get("enable_cross_frame_attn", False),
@@ -493,8 +526,10 @@ def _conv_bias_nhwc(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
 
 def _sampler_ok(module: nn.Module, x: torch.Tensor) -> bool:
     conv = getattr(module, "conv", None)
+    # Downsample2D(padding=0) pads (0, 1, 0, 1) before its convolution (diffusers): not the plain conv call below
     return (_fast_ok(x, module) and isinstance(conv, nn.Conv2d) and conv.padding_mode == "zeros" and x.dim() == 4
-            and ops.is_channels_last(x) and x.shape[1] % 8 == 0)
+            and ops.is_channels_last(x) and x.shape[1] % 8 == 0
+            and (type(module).__name__ != "Downsample2D" or conv.padding not in ((0, 0), 0)))
 
 
 def _make_upsample_forward(module: nn.Module, original: Callable):
@@ -502,7 +537,7 @@ def _make_upsample_forward(module: nn.Module, original: Callable):
     @functools.wraps(original)
     def forward(x, output_size=None, *args, **kwargs):
         if output_size is not None or not _sampler_ok(module, x):
-            return original(x, output_size, *args, **kwargs)
+            return _fallback("upsample", original, x, output_size, *args, **kwargs)
         return _conv_bias_nhwc(module.conv, ops.upsample2x_nhwc(x))
 
     return forward
@@ -512,7 +547,7 @@ def _make_downsample_forward(module: nn.Module, original: Callable):
     @functools.wraps(original)
     def forward(x, *args, **kwargs):
         if not _sampler_ok(module, x):
-            return original(x, *args, **kwargs)
+            return _fallback("downsample", original, x, *args, **kwargs)
         return _conv_bias_nhwc(module.conv, x)
 
     return forward
@@ -529,7 +564,7 @@ def _make_out_norm_forwards(norm: nn.GroupNorm, act: nn.Module, norm_forward: Ca
             state["fused"] = True
             return ops.group_norm_nhwc(x, norm.weight, norm.bias, norm.num_groups, norm.eps, 1, silu=True)
         state["fused"] = False
-        return norm_forward(x)
+        return _fallback("conv_norm_out", norm_forward, x)
 
     @functools.wraps(act_forward)
     def act_fwd(x):

@@ -77,6 +77,19 @@ def _split_heads(t: torch.Tensor, heads: int) -> torch.Tensor:
     return t.view(b, n, heads, c // heads).transpose(1, 2)
 
 
+def prepare_attention_mask(mask: torch.Tensor, target_length: int, batch: int, heads: int) -> torch.Tensor:
+    """diffusers 0.25 ``Attention.prepare_attention_mask`` followed by the view ``AttnProcessor2_0`` takes of it:
+    a (B, 1, L) or (B, L) additive mask, padded to ``target_length`` keys, repeated per head ->
+    (B, heads, 1 or Sq, L) for ``F.scaled_dot_product_attention``."""
+    if mask.dim() == 2:
+        mask = mask[:, None, :]
+    if mask.shape[-1] < target_length:   # (diffusers pads by target_length itself, which never matches; pad the rest)
+        mask = F.pad(mask, (0, target_length - mask.shape[-1]), value=0.0)
+    if mask.shape[0] == batch:
+        mask = mask.repeat_interleave(heads, dim=0)   # (B * heads, q, L), head index fastest as in diffusers
+    return mask.view(batch, heads, -1, mask.shape[-1])
+
+
 class AttnProcessor2_0:
     """softmax(q k^T / sqrt(d)) v through ``F.scaled_dot_product_attention`` followed by ``to_out``."""
 
@@ -85,7 +98,7 @@ class AttnProcessor2_0:
         batch = hidden_states.shape[0]
         context = hidden_states if encoder_hidden_states is None else encoder_hidden_states
         if attention_mask is not None:
-            attention_mask = attention_mask.view(batch, attn.heads, -1, attention_mask.shape[-1])
+            attention_mask = prepare_attention_mask(attention_mask, context.shape[1], batch, attn.heads)
         q = _split_heads(attn.to_q(hidden_states), attn.heads)
         k = _split_heads(attn.to_k(context), attn.heads)
         v = _split_heads(attn.to_v(context), attn.heads)

@@ -186,9 +186,12 @@ class Downsample2D(nn.Module):
     def __init__(self, channels: int, use_conv: bool = True, out_channels: Optional[int] = None, padding: int = 1,
                  name: str = "conv"):
         super().__init__()
+        self.padding = padding
         self.conv = nn.Conv2d(channels, out_channels or channels, 3, stride=2, padding=padding)
 
     def forward(self, x, scale: float = 1.0):
+        if self.padding == 0:   # diffusers: asymmetric (right / bottom) zero padding in front of the unpadded conv
+            x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
         return self.conv(x)
 
 

@@ -60,8 +60,24 @@ class BlockState:
         self.first_frame_source = None
 
 
+_CACHE_EPOCH = [0]   # bumped by invalidate_caches(): part of every packed-weight cache key (here and in fastpath.py)
+
+
+def invalidate_caches() -> None:
+    """Drop every packed / augmented weight copy held by the processors and the module-level fast path.
+
+    The caches key on ``(data_ptr, _version)`` of their source parameters, which catches ``load_state_dict``,
+    ``.to()``, optimizer steps and ordinary in-place ops -- but **not** writes through ``.data`` (``p.data.zero_()``,
+    ``p.data.copy_()`` as EMA ``copy_to`` does; the reference's own ``from_transformer2d_model`` zero-initialises
+    ``to_out`` that way, src/modules/i2v_adapter.py:142-143): those leave ``_version`` untouched.  Call this (or
+    ``Installation.invalidate_caches()``) after such an update.  ``install`` also registers a ``load_state_dict``
+    post-hook that calls it."""
+    _CACHE_EPOCH[0] += 1
+
+
 class _PackedWeights:
-    """Cache of concatenated weight matrices, invalidated when any source parameter changes."""
+    """Cache of concatenated weight matrices, invalidated when any source parameter changes (see
+    ``invalidate_caches`` for the one kind of change it cannot see)."""
 
     def __init__(self):
         self._key = None
@@ -72,9 +88,10 @@ class _PackedWeights:
         return None if t is None else (t.data_ptr(), t._version, t.dtype, t.device, tuple(t.shape))
 
     def get(self, sources: List[Optional[torch.Tensor]], build):
-        key = tuple(self._sig(s) for s in sources)
+        key = (_CACHE_EPOCH[0],) + tuple(self._sig(s) for s in sources)
         if key != self._key:
-            self._val = build()
+            with torch.no_grad():   # the packed copy is a constant of the forward-only kernels, never a graph node
+                self._val = build()
             self._key = key
         return self._val
 
@@ -113,7 +130,14 @@ def _augmented_projection(mods, kinds, heads: int, d: int, scale: float):
     return torch.cat(ws).to(dt).contiguous(), torch.cat(bs).to(dt).contiguous()
 
 
-def _check_supported(attn, attention_mask, what: str) -> None:
+def _check_supported(attn, attention_mask, what: str, hidden_states: Optional[torch.Tensor] = None) -> None:
+    if torch.is_grad_enabled() and ((hidden_states is not None and hidden_states.requires_grad)
+                                    or any(p.requires_grad for p in attn.parameters())):
+        # the kernels are forward-only (no autograd.Function): with grad mode on, to_q / to_out of the trainable
+        # I2V-Adapter (src/train_i2v_adapter.py) would silently receive no gradient
+        raise RuntimeError(
+            f"{what}: the B200 attention kernels are inference-only. Call the model under torch.no_grad() / "
+            f"torch.inference_mode(), or uninstall() the B200 processors before training.")
     if attention_mask is not None:
         raise NotImplementedError(
             f"{what}: attention_mask is not supported by the B200 kernels (the reference UNet always passes None, "
@@ -195,7 +219,7 @@ class B200AttnProcessor:
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
                  scale: float = 1.0, **kwargs):
-        _check_supported(attn, attention_mask, type(self).__name__)
+        _check_supported(attn, attention_mask, type(self).__name__, hidden_states)
         residual = hidden_states
         x, shape4 = _to_3d(hidden_states)
         B, S, _ = x.shape
@@ -263,7 +287,7 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
                  and getattr(attn, "rescale_output_factor", 1.0) == 1.0)
         if not fused:
             return super().__call__(attn, hidden_states, encoder_hidden_states, attention_mask, temb, scale, **kwargs)
-        _check_supported(attn, attention_mask, type(self).__name__)
+        _check_supported(attn, attention_mask, type(self).__name__, hidden_states)
         xa = self.sibling
         _check_supported(xa, None, type(self).__name__)
         x = hidden_states
@@ -286,8 +310,7 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
                                          (so.bias if so.bias is not None else 0) +
                                          (xo.bias if xo.bias is not None else 0)))
         first = x[0::Fr]  # frame 0 of every video: rows b*F (reference :484), no F-times repeat (:485)
-        if (self.augmented and d == ops.AUG_D and x.dtype == torch.bfloat16 and self.mode != MODE_GENERIC
-                and st.first_frame_source is None):
+        if self.augmented and d == ops.AUG_D and x.dtype == torch.bfloat16 and self.mode != MODE_GENERIC:
             # level 0 (d = 40): the projections emit the augmented layout (scale folded into the query weights, ones
             # column in K and V, head dim padded to 48) that lets the kernel skip the scale FMA and the row-sum adds
             dp = ops.AUG_DPAD
@@ -296,7 +319,12 @@ class B200SpatialAttnProcessor(B200AttnProcessor):
             wxa = self._w_x_aug.get([xa.to_k.weight, xa.to_v.weight, xa.to_k.bias, xa.to_v.bias],
                                     lambda: _augmented_projection([xa.to_k, xa.to_v], ["kv", "kv"], H, d, attn.scale))
             y = F.linear(x, wa[0], wa[1]).view(BF, S, 4, H, dp)
-            kvx = F.linear(first, wxa[0], wxa[1]).view(BF // Fr, S, 2, H, dp)
+            if st.first_frame_source is not None:  # frame shard: the owner of global frame 0 projects, one broadcast
+                kvx = st.first_frame_source.broadcast_from_first_frame_owner(
+                    lambda: F.linear(first, wxa[0], wxa[1]), (BF // Fr, S, 2 * H * dp), x.dtype, x.device)
+            else:
+                kvx = F.linear(first, wxa[0], wxa[1])
+            kvx = kvx.view(BF // Fr, S, 2, H, dp)
             o = ops.fused_self_xframe_aug(y[:, :, 0], y[:, :, 1], y[:, :, 2], y[:, :, 3], kvx[:, :, 0], kvx[:, :, 1],
                                           Fr, d)
             out = _out_proj(self, attn, o.view(BF, S, 2 * inner), w_out[0], w_out[1], kwargs)
@@ -335,7 +363,7 @@ class B200CrossFrameAttnProcessor:
         if st is not None and st.cross_done:
             st.cross_done = False
             return hidden_states.new_zeros((1,) * hidden_states.dim()).expand_as(hidden_states)
-        _check_supported(attn, attention_mask, type(self).__name__)
+        _check_supported(attn, attention_mask, type(self).__name__, hidden_states)
         x = hidden_states
         B, S, _ = x.shape
         H = attn.heads
@@ -351,7 +379,10 @@ class B200CrossFrameAttnProcessor:
                            lambda: (torch.cat([attn.to_k.weight, attn.to_v.weight]),
                                     _cat_bias([attn.to_k.bias, attn.to_v.bias], [inner] * 2, attn.to_k.weight)))
         q = attn.to_q(x).view(B, S, H, d)
-        if st is not None and st.first_frame_source is not None and group > 1:
+        if (st is not None and st.first_frame_source is not None and st.enable_cross_frame
+                and encoder_hidden_states is not None and ctx.shape[0] * group == B):
+            # frame shard: the rows of `ctx` are this rank's *local* first frames; global frame 0 lives on its owner.
+            # (Also with one frame per rank, where group == 1 and the local rows would otherwise pass for frame 0.)
             kv = st.first_frame_source.broadcast_from_first_frame_owner(
                 lambda: F.linear(ctx, w[0], w[1]), (ctx.shape[0], ctx.shape[1], 2 * inner), x.dtype, x.device)
         else:
@@ -391,7 +422,7 @@ class B200IPAdapterAttnProcessor(nn.Module):
 
     def forward(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
                 scale: float = 1.0, **kwargs):
-        _check_supported(attn, attention_mask, type(self).__name__)
+        _check_supported(attn, attention_mask, type(self).__name__, hidden_states)
         residual = hidden_states
         x, shape4 = _to_3d(hidden_states)
         B, S, _ = x.shape
@@ -444,7 +475,7 @@ class B200TemporalAttnProcessor:
             out = self._generic(attn, hidden_states, encoder_hidden_states, attention_mask, temb, scale, **kwargs)
             self.fused_residual, self.deferred_bias = self._generic.fused_residual, self._generic.deferred_bias
             return out
-        _check_supported(attn, attention_mask, type(self).__name__)
+        _check_supported(attn, attention_mask, type(self).__name__, hidden_states)
         x = hidden_states
         N, Fr, _ = x.shape
         H = attn.heads
@@ -475,6 +506,11 @@ class Installation:
         self.context = context
         self.processors = processors
         self.undo_forwards = undo_forwards or []
+
+    @staticmethod
+    def invalidate_caches() -> None:
+        """See ``processors.invalidate_caches``: needed after parameter writes through ``.data`` only."""
+        invalidate_caches()
 
     def uninstall(self) -> None:
         for fn in reversed(self.undo_forwards):
@@ -598,6 +634,11 @@ def install(unet: nn.Module, mode: int = MODE_AUTO, fuse_cross_frame: bool = Tru
 
         hooks.append(unet.register_forward_pre_hook(unet_pre, with_kwargs=True))
         hooks.append(unet.register_forward_hook(unet_post))
+
+    if hasattr(unet, "register_load_state_dict_post_hook"):
+        # load_state_dict copies through no-grad copy_ (bumps _version) on most paths, but assign=True and custom
+        # loaders swap .data: drop the packed copies after any load so stale weights can never be used
+        hooks.append(unet.register_load_state_dict_post_hook(lambda module, incompatible: invalidate_caches()))
 
     apply_attn_processors(unet, new)
     undo_forwards = []

@@ -201,6 +201,17 @@ int i2v_upsample2x_nhwc(const void* x, void* out, int N, int h, int w, int C, vo
  * tcgen05 single-tile kernel instead of the streaming kernel, key 6: streaming-kernel configuration. */
 int i2v_set_tuning(int key, int value);
 
+/* Launch timing for bench.py ("the dominant kernel timed live with CUDA events on the launching
+ * stream").  i2v_prof_arm(kind, a, b, n): the next n launches of kernel class `kind` whose shape matches (a, b)
+ * (0 = any) are bracketed by a cudaEvent pair recorded by the library right around the launch (after tensor-map
+ * encoding; while the stream is captured into a CUDA graph the records become external event nodes, re-recorded by
+ * every replay).  n <= 0 disarms.  i2v_prof_read(kind, ms, cap): elapsed ms of the recorded pairs (the caller has
+ * synchronised); returns their number.
+ *   kind 1: dense attention (a = query rows per batch entry, b = batch)      2: temporal (a = positions, b = d)
+ *   kind 3: IP-Adapter attention (a = query rows, b = batch)                  4: token GEMMs (a = rows, b = N) */
+int i2v_prof_arm(int kind, long long match_a, long long match_b, int max_pairs);
+int i2v_prof_read(int kind, float* ms_out, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

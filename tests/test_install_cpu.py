@@ -48,7 +48,17 @@ def test_installed_processors_fail_loudly_on_cpu():
     unet = make_unet()
     install(unet)
     x = torch.randn(1, 2, 4, 16, 16)
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        unet(x, 10, True, torch.randn(1, 5, TINY_CFG["cross_attention_dim"]))
+
+
+def test_installed_processors_refuse_grad_mode():
+    """The kernels are forward-only: with grad mode on and trainable parameters (the reference trains to_q / to_out of
+    the adapter, src/train_i2v_adapter.py) the processors must raise instead of silently dropping the gradient."""
+    unet = make_unet()
+    install(unet)
+    x = torch.randn(1, 2, 4, 16, 16)
+    with pytest.raises(RuntimeError, match="inference-only"):
         unet(x, 10, True, torch.randn(1, 5, TINY_CFG["cross_attention_dim"]))
 
 
@@ -84,3 +94,42 @@ def test_packed_weight_cache_invalidates_on_update():
     w.data = torch.randn(4, 4)  # storage replaced (.to(), new checkpoint)
     cache.get([w], build)
     assert len(calls) == 3
+
+
+def test_invalidate_caches_catches_writes_through_data():
+    """``p.data.zero_()`` (the reference's own zero-init, src/modules/i2v_adapter.py:142-143) does not bump
+    ``_version``: the explicit epoch is the documented way to drop the packed copies."""
+    from i2v_adapter_unofficial_b200.processors import Installation, invalidate_caches
+
+    w = torch.nn.Parameter(torch.randn(4, 4))
+    cache = _PackedWeights()
+    calls = []
+    build = lambda: calls.append(1) or w.detach().clone()  # noqa: E731
+    a = cache.get([w], build)
+    assert not a.requires_grad
+    w.data.zero_()
+    assert cache.get([w], build) is a          # invisible to the (data_ptr, _version) key ...
+    invalidate_caches()
+    b = cache.get([w], build)                  # ... until the epoch moves
+    assert len(calls) == 2 and torch.count_nonzero(b) == 0
+    Installation.invalidate_caches()
+    cache.get([w], build)
+    assert len(calls) == 3
+
+
+def test_packed_weights_are_built_without_autograd_graph():
+    w = torch.nn.Parameter(torch.randn(4, 4))
+    cache = _PackedWeights()
+    with torch.enable_grad():
+        v = cache.get([w], lambda: torch.cat([w, w]))
+    assert v.grad_fn is None and not v.requires_grad
+
+
+def test_load_state_dict_after_install_invalidates_caches():
+    from i2v_adapter_unofficial_b200 import processors
+
+    unet = make_unet()
+    install(unet)
+    before = processors._CACHE_EPOCH[0]
+    unet.load_state_dict(unet.state_dict())
+    assert processors._CACHE_EPOCH[0] > before
