@@ -47,6 +47,9 @@ EXPORTED_SYMBOLS = (
     "i2v_gn_nhwc_cat",
     "i2v_rows_residual",
     "i2v_rows_residual_bias",
+    "i2v_gn_nhwc_sums",
+    "i2v_gn_nhwc_apply",
+    "i2v_rows_residual_sharded",
 )
 
 
@@ -131,6 +134,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_gn_nhwc_cat.argtypes = [p, p, i, p, p, p, p, p, i, i, i, i, i, f, i, i, p]
     lib.i2v_rows_residual.restype = i
     lib.i2v_rows_residual.argtypes = [p, p, p, i, i, i, i, p]
+    lib.i2v_gn_nhwc_sums.restype = i
+    lib.i2v_gn_nhwc_sums.argtypes = [p, p, p, i, i, i, i, i, p]
+    lib.i2v_gn_nhwc_apply.restype = i
+    lib.i2v_gn_nhwc_apply.argtypes = [p, p, p, p, p, p, i, i, i, i, i, i, i, i, p]
+    lib.i2v_rows_residual_sharded.restype = i
+    lib.i2v_rows_residual_sharded.argtypes = [p, p, p, i, i, i, i, i, p]
     lib.i2v_rows_residual_bias.restype = i
     lib.i2v_rows_residual_bias.argtypes = [p, p, p, p, i, i, i, i, p]
 

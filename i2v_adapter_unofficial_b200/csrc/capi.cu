@@ -1017,8 +1017,37 @@ int i2v_gn_nhwc(const void* x, const void* add, const void* w, const void* b, vo
   return i2v_gn_nhwc_cat(x, nullptr, C, add, w, b, out, scratch, N, S, C, G, fg, eps, silu, perm, stream);
 }
 
+// phases: 1 = statistics (+ finalize), 2 = apply, 3 = both.  `ext_stats` (phase 1 with raw sums / phase 2): a caller-owned
+// [N / fg, G, 2] float buffer -- the frame partitioner reduces the raw sums over the ranks in between.
+static int gn_nhwc_phased(int phases, float* ext_stats, int world, const void* x, const void* x2, int C1, const void* add,
+                          const void* w, const void* b, void* out, float* scratch, int N, int S, int C, int G, int fg,
+                          float eps, int silu, int perm, void* stream);
+
 int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, const void* w, const void* b, void* out,
                     float* scratch, int N, int S, int C, int G, int fg, float eps, int silu, int perm, void* stream) {
+  if (perm != 0 && perm != 1) return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc: perm must be 0 or 1 (got %d)", perm);
+  return gn_nhwc_phased(3, nullptr, 1, x, x2, C1, add, w, b, out, scratch, N, S, C, G, fg, eps, silu, perm, stream);
+}
+
+int i2v_gn_nhwc_sums(const void* x, float* sums, float* scratch, int N, int S, int C, int G, int fg, void* stream) {
+  if (!sums) return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc_sums: null output");
+  return gn_nhwc_phased(1, sums, 1, x, nullptr, C, nullptr, x, x, const_cast<void*>(x), scratch, N, S, C, G, fg, 0.f, 0, 0,
+                        stream);
+}
+
+int i2v_gn_nhwc_apply(const void* x, const void* add, const void* w, const void* b, void* out, const float* mean_rstd,
+                      int N, int S, int C, int G, int fg, int silu, int perm, int world, void* stream) {
+  if (!mean_rstd) return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc_apply: null statistics");
+  if (perm < 0 || perm > 2) return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc_apply: perm must be 0, 1 or 2 (got %d)", perm);
+  if (perm == 2 && (world <= 0 || S % world))
+    return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc_apply: %d positions are not divisible by the %d ranks", S, world);
+  return gn_nhwc_phased(2, const_cast<float*>(mean_rstd), perm == 2 ? world : 1, x, nullptr, C, add, w, b, out,
+                        const_cast<float*>(mean_rstd), N, S, C, G, fg, 0.f, silu, perm, stream);
+}
+
+static int gn_nhwc_phased(int phases, float* ext_stats, int world, const void* x, const void* x2, int C1, const void* add,
+                          const void* w, const void* b, void* out, float* scratch, int N, int S, int C, int G, int fg,
+                          float eps, int silu, int perm, void* stream) {
   if (x2 && (C1 <= 0 || C1 >= C || C1 % 8 || !aligned16(x2)))
     return fail(I2V_ERR_BAD_SHAPE, "gn_nhwc_cat: the first source needs 0 < C1 < C, C1 %% 8 == 0 and a 16-byte aligned second source (C1=%d C=%d)", C1, C);
   if (N <= 0 || S <= 0 || C <= 0 || G <= 0 || fg <= 0 || C % G || C % 8 || N % fg)
@@ -1036,6 +1065,8 @@ int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, cons
   P.x2 = (const __nv_bfloat16*)x2; P.C1 = x2 ? C1 : C;
   P.w = (const __nv_bfloat16*)w; P.b = (const __nv_bfloat16*)b;
   P.N = N; P.S = S; P.C = C; P.G = G; P.fg = fg; P.eps = eps; P.silu = silu; P.perm = perm;
+  P.world = world;
+  P.raw = (phases == 1 && ext_stats) ? 1 : 0;
   // row chunks per image: one full wave of CTAs and no second, partial one (statistics: four 256-thread CTAs per SM;
   // apply: two CTAs of up to 512 threads per SM) -- rounding the count up cost a whole extra wave for 16 CTAs
   auto chunks = [&](int ctas_per_sm) {
@@ -1048,15 +1079,19 @@ int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, cons
   P.rows_per_chunk = (S + ch - 1) / ch;
   P.CH = (S + P.rows_per_chunk - 1) / P.rows_per_chunk;
   P.partial = scratch;
-  P.stats = scratch + (long long)N * kGnMaxChunks * G * 2;
+  P.stats = ext_stats ? ext_stats : scratch + (long long)N * kGnMaxChunks * G * 2;
   const int VC = C / 8;
-  const int block = VC > 256 ? (VC + 31) / 32 * 32 : 256;
-  dim3 grid(P.CH, N);
-  i2v::gn_stats_nhwc_kernel<<<grid, block, 2 * C * sizeof(float), (cudaStream_t)stream>>>(P);
-  CUDA_TRY(cudaGetLastError());
-  const int vg = (N / fg) * G;
-  i2v::gn_finalize_kernel<<<(vg + 7) / 8, 256, 0, (cudaStream_t)stream>>>(P);   // one warp per (video, group)
-  CUDA_TRY(cudaGetLastError());
+  if (phases & 1) {
+    const int block = VC > 256 ? (VC + 31) / 32 * 32 : 256;
+    dim3 grid(P.CH, N);
+    i2v::gn_stats_nhwc_kernel<<<grid, block, 2 * C * sizeof(float), (cudaStream_t)stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    const int vg = (N / fg) * G;
+    i2v::gn_finalize_kernel<<<(vg + 7) / 8, 256, 0, (cudaStream_t)stream>>>(P);   // one warp per (video, group)
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(2);
+  }
+  if (!(phases & 2)) return 0;
   // thread = (channel vector, row phase): as many row phases as fit 512 threads
   const int rpp = VC >= 512 ? 1 : 512 / VC;
   const int ablock = (VC * rpp + 31) / 32 * 32;
@@ -1066,12 +1101,27 @@ int i2v_gn_nhwc_cat(const void* x, const void* x2, int C1, const void* add, cons
   dim3 agrid((S + PA.rows_per_chunk - 1) / PA.rows_per_chunk, N);
   i2v::gn_apply_rows_kernel<<<agrid, ablock, 0, (cudaStream_t)stream>>>(PA);
   CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(3);
+  g_launches.fetch_add(1);
   return 0;
 }
 
+static int rows_residual_impl(const void* y, const void* res, const void* bias, void* out, int N, int S, int C, int fg,
+                              int world, void* stream);
+
 int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, void* out, int N, int S, int C, int fg,
                            void* stream) {
+  return rows_residual_impl(y, res, bias, out, N, S, C, fg, 1, stream);
+}
+
+int i2v_rows_residual_sharded(const void* y, const void* res, void* out, int N, int S, int C, int fg, int world,
+                              void* stream) {
+  if (world <= 0 || S % world) return fail(I2V_ERR_BAD_SHAPE, "rows_residual_sharded: %d positions, %d ranks", S, world);
+  if (!res) return fail(I2V_ERR_BAD_SHAPE, "rows_residual_sharded: null residual");
+  return rows_residual_impl(y, res, nullptr, out, N, S, C, fg, world, stream);
+}
+
+static int rows_residual_impl(const void* y, const void* res, const void* bias, void* out, int N, int S, int C, int fg,
+                              int world, void* stream) {
   if (N <= 0 || S <= 0 || C <= 0 || fg <= 0 || C % 8 || N % fg)
     return fail(I2V_ERR_BAD_SHAPE, "rows_residual: bad shape N=%d S=%d C=%d fg=%d", N, S, C, fg);
   if (!y || !out || (!res && !bias)) return fail(I2V_ERR_BAD_SHAPE, "rows_residual: null pointer");
@@ -1084,7 +1134,7 @@ int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, voi
   i2v::RowsResidualParams P;
   P.y = (const __nv_bfloat16*)y; P.res = (const __nv_bfloat16*)res; P.out = (__nv_bfloat16*)out;
   P.bias = (const __nv_bfloat16*)bias;
-  P.N = N; P.S = S; P.C = C; P.fg = fg;
+  P.N = N; P.S = S; P.C = C; P.fg = fg; P.world = world;
   const long long rows = (long long)N * S;
   long long blocks = (rows + 7) / 8;
   if (blocks > 8LL * di->sms) blocks = 8LL * di->sms;

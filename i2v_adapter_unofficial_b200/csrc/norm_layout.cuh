@@ -476,9 +476,19 @@ struct GnNhwcParams {
   const __nv_bfloat16* w;
   const __nv_bfloat16* b;
   int N, S, C, G, fg, CH, rows_per_chunk;
-  int silu, perm;
-  float eps;
+  int silu, perm;   // perm = 2: [W, V, S/W, fg, C] -- position-major rows grouped by the W destination ranks of the
+  float eps;        //   frame partitioner's all-to-all (send buffer written directly, no pack pass)
+  int world = 1;    // W of perm = 2
+  int raw = 0;      // finalize writes the raw (sum, sum of squares) instead of (mean, rstd): frame-sharded statistics
 };
+
+// output row of (video v, position rr, local frame f) in the three layouts of the NHWC GroupNorm family
+__device__ __forceinline__ long long gn_out_row(int perm, int n, int v, int f, int rr, int S, int fg, int V, int world) {
+  if (perm == 0) return (long long)n * S + rr;
+  if (perm == 1) return ((long long)v * S + rr) * fg + f;
+  const int Sl = S / world, g = rr / Sl, sl = rr - g * Sl;
+  return ((((long long)g * V + v) * Sl) + sl) * fg + f;
+}
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
@@ -567,6 +577,11 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnNhwcParams P) 
   a = warp_sum(a);
   b = warp_sum(b);
   if (lane == 0) {
+    if (P.raw) {
+      P.stats[2 * i] = a;
+      P.stats[2 * i + 1] = b;
+      return;
+    }
     const float cnt = (float)P.fg * (float)(P.C / P.G) * (float)P.S;
     const float mean = a / cnt;
     P.stats[2 * i] = mean;
@@ -617,7 +632,7 @@ __global__ void __launch_bounds__(512, 2) gn_apply_rows_kernel(const GnNhwcParam
     for (int u = 0; u < 4; ++u) {
       const int rr = r + u * rpp;
       if (rr >= r1) break;
-      const long long orow = P.perm ? (((long long)v * P.S + rr) * P.fg + f) : ((long long)n * P.S + rr);
+      const long long orow = gn_out_row(P.perm, n, v, f, rr, P.S, P.fg, P.N / P.fg, P.world);
       const uint32_t ww[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
       uint32_t o[4];
 #pragma unroll
@@ -645,6 +660,7 @@ struct RowsResidualParams {
   const __nv_bfloat16* bias;   // [C] or null: added per channel (a convolution / projection bias folded into this pass)
   __nv_bfloat16* out;
   int N, S, C, fg;
+  int world = 1;   // > 1: y is the frame partitioner's receive buffer [W, V, S/W, fg, C] (perm = 2 of the GroupNorm family)
 };
 
 __global__ void __launch_bounds__(256) rows_residual_kernel(const RowsResidualParams P) {
@@ -654,7 +670,8 @@ __global__ void __launch_bounds__(256) rows_residual_kernel(const RowsResidualPa
   for (long long row = (long long)blockIdx.x * nwarps + warp; row < rows; row += (long long)gridDim.x * nwarps) {
     const int n = (int)(row / P.S), s = (int)(row - (long long)n * P.S);
     const int v = n / P.fg, f = n - v * P.fg;
-    const uint4* ysrc = reinterpret_cast<const uint4*>(P.y + (((long long)v * P.S + s) * P.fg + f) * P.C);
+    const uint4* ysrc = reinterpret_cast<const uint4*>(
+        P.y + gn_out_row(P.world > 1 ? 2 : 1, n, v, f, s, P.S, P.fg, P.N / P.fg, P.world) * P.C);
     const uint4* rsrc = P.res ? reinterpret_cast<const uint4*>(P.res + row * P.C) : nullptr;   // null: out = y + bias
     uint4* dst = reinterpret_cast<uint4*>(P.out + row * P.C);
     for (int cv = lane; cv < VC; cv += 32) {

@@ -370,6 +370,62 @@ def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, g
     return out
 
 
+def group_norm_nhwc_sums(x: torch.Tensor, groups: int, frames_per_stat: int) -> torch.Tensor:
+    """Raw per-(video, group) (sum, sum of squares) over the ``frames_per_stat`` local frames of a channels-last
+    activation x (N, C, h, w): fp32 [N / F, groups, 2].  First half of the frame-sharded GroupNorm."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and is_channels_last(x)):
+        raise RuntimeError("group_norm_nhwc_sums: needs a CUDA bf16 channels-last tensor (no CPU fallback)")
+    N, C, h, w = x.shape
+    lib = _lib.load()
+    scratch = torch.empty((int(lib.i2v_gn_nhwc_scratch_floats(N, groups)),), dtype=torch.float32, device=x.device)
+    sums = torch.empty((N // frames_per_stat, groups, 2), dtype=torch.float32, device=x.device)
+    with _on_device(x.device):
+        _lib.check(lib.i2v_gn_nhwc_sums(x.data_ptr(), sums.data_ptr(), scratch.data_ptr(), N, h * w, C, groups,
+                                        frames_per_stat, _stream(x.device)))
+    return sums
+
+
+def group_norm_nhwc_apply(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, mean_rstd: torch.Tensor,
+                          groups: int, frames_per_stat: int, world: int = 1, silu: bool = False) -> torch.Tensor:
+    """Second half: y = (x - mean) * rstd * w + b with caller-provided fp32 statistics [N / F, groups, 2].
+    ``world == 1``: the motion module's [N/F * S, F, C] token layout; ``world > 1``: the frame partitioner's
+    all-to-all send buffer [W, V, S / W, F_local, C]."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and is_channels_last(x)):
+        raise RuntimeError("group_norm_nhwc_apply: needs a CUDA bf16 channels-last tensor (no CPU fallback)")
+    N, C, h, w = x.shape
+    S, fg = h * w, frames_per_stat
+    V = N // fg
+    if mean_rstd.shape != (V, groups, 2) or mean_rstd.dtype != torch.float32 or not mean_rstd.is_contiguous():
+        raise ValueError(f"mean_rstd must be a contiguous fp32 [{V}, {groups}, 2] tensor")
+    if world > 1:
+        out = torch.empty((world, V, S // world, fg, C), dtype=x.dtype, device=x.device)
+    else:
+        out = torch.empty((V * S, fg, C), dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    with _on_device(x.device):
+        _lib.check(lib.i2v_gn_nhwc_apply(x.data_ptr(), None, weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                         mean_rstd.data_ptr(), N, S, C, groups, fg, int(silu), 2 if world > 1 else 1,
+                                         world, _stream(x.device)))
+    return out
+
+
+def sharded_positions_to_nhwc_residual(y: torch.Tensor, residual: torch.Tensor, frames_per_stat: int,
+                                       world: int) -> torch.Tensor:
+    """Frame partitioner, way back: y [W, V, S / W, F_local, C] (all-to-all receive buffer) + channels-last residual
+    (N, C, h, w) -> channels-last (N, C, h, w)."""
+    if not (y.is_cuda and y.dtype == torch.bfloat16 and y.is_contiguous() and is_channels_last(residual)):
+        raise RuntimeError("sharded_positions_to_nhwc_residual: needs CUDA bf16 tensors, residual channels-last")
+    N, C, h, w = residual.shape
+    if y.numel() != residual.numel():
+        raise ValueError(f"y {tuple(y.shape)} and residual {tuple(residual.shape)} differ in size")
+    out = torch.empty_like(residual)
+    lib = _lib.load()
+    with _on_device(y.device):
+        _lib.check(lib.i2v_rows_residual_sharded(y.data_ptr(), residual.data_ptr(), out.data_ptr(), N, h * w, C,
+                                                 frames_per_stat, world, _stream(y.device)))
+    return out
+
+
 def positions_to_nhwc_residual(y: torch.Tensor, residual: torch.Tensor, frames_per_stat: int) -> torch.Tensor:
     """Motion module, way back: y [N/F * h*w, F, C] + channels-last residual (N, C, h, w) -> channels-last (N, C, h, w)."""
     if not (y.is_cuda and y.dtype == torch.bfloat16 and y.is_contiguous() and is_channels_last(residual)):

@@ -189,6 +189,37 @@ class FramePartitioner:
         self.root = dist.get_global_rank(group, 0) if group is not None else 0
         self._undo: List[Callable[[], None]] = []
         self.stats = {"broadcasts": 0, "all_to_alls": 0, "stat_gathers": 0}
+        self._timing: Optional[Dict[str, list]] = None   # bench.py: CUDA-event pairs around every collective
+
+    # -- collective timing (bench.py's frame-sharded leg) -------------------------------------------------------
+    def start_timing(self) -> None:
+        self._timing = {"broadcast": [], "all_to_all": [], "stat_gather": []}
+
+    def _collective(self, kind: str, fn: Callable[[], Any], nbytes: float):
+        """Run one collective; when timing is on, bracket it with events on the current stream (the NCCL work is
+        stream-ordered with it) and remember the bytes this rank moves."""
+        if self._timing is None or not torch.cuda.is_available():
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self._timing[kind].append((e0, e1, float(nbytes)))
+        return out
+
+    def timing_summary(self, steps: int) -> Dict[str, Any]:
+        """Per step and per kind: calls, device ms inside the collectives (includes waiting for the slowest rank),
+        bytes this rank sends, and the resulting GB/s."""
+        torch.cuda.synchronize()
+        out: Dict[str, Any] = {}
+        for kind, pairs in (self._timing or {}).items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in pairs)
+            nbytes = sum(n for _, _, n in pairs)
+            out[kind] = dict(calls_per_step=len(pairs) / max(steps, 1), ms_per_step=ms / max(steps, 1),
+                             bytes_per_step_per_rank=nbytes / max(steps, 1),
+                             gb_per_s_per_rank=(nbytes / 1e9) / (ms / 1e3) if ms > 0 else None)
+        self._timing = None
+        return out
 
     # -- frame axis helpers ------------------------------------------------------------------------------------
     @property
@@ -214,7 +245,8 @@ class FramePartitioner:
         t = compute().contiguous() if self.owns_first_frame else torch.empty(shape, dtype=dtype, device=device)
         if tuple(t.shape) != tuple(shape):
             raise ValueError(f"first-frame tensor has shape {tuple(t.shape)}, expected {tuple(shape)}")
-        dist.broadcast(t, src=self.root, group=self.group)
+        self._collective("broadcast", lambda: dist.broadcast(t, src=self.root, group=self.group),
+                         t.numel() * t.element_size() if self.owns_first_frame else 0)
         self.stats["broadcasts"] += 1
         return t
 
@@ -227,6 +259,8 @@ class FramePartitioner:
         if bf % f:
             raise ValueError(f"Batch size {bf} must be divisible by the number of frames {f}.")
         V, S, G = bf // f, h * w, self.world
+        if self._library_path_ok(module, hidden_states, S):
+            return self._temporal_forward_library(module, hidden_states, f, **kw)
         residual = hidden_states
         x = sharded_group_norm(hidden_states.view(V, f, C, h, w), module.norm, self.group)
         self.stats["stat_gathers"] += 1
@@ -243,6 +277,55 @@ class FramePartitioner:
         local = positions_to_frames(back, self.group, self.allow_torch_layout)            # [V, f, S, C]
         self.stats["all_to_alls"] += 1
         out = local.view(V, f, h, w, C).permute(0, 1, 4, 2, 3).reshape(bf, C, h, w) + residual
+        if kw.get("return_dict", True):
+            from .hostmodel.i2v_adapter import _Sample
+            return _Sample(out)
+        return (out,)
+
+    def _library_path_ok(self, module: nn.Module, x: torch.Tensor, S: int) -> bool:
+        norm = module.norm
+        return (x.is_cuda and x.dtype == torch.bfloat16 and ops.is_channels_last(x) and not x.is_contiguous()
+                and isinstance(norm, nn.GroupNorm) and norm.affine and norm.weight.dtype == x.dtype
+                and x.shape[1] % 8 == 0 and x.shape[1] <= 4096 and S % self.world == 0
+                and isinstance(module.proj_in, nn.Linear) and not torch.is_grad_enabled())
+
+    def _temporal_forward_library(self, module: nn.Module, hidden_states: torch.Tensor, f: int, **kw):
+        """The same exchange on the library's channels-last kernels: raw GroupNorm sums -> all-reduce of
+        ``2 * V * groups`` floats -> the apply pass writes the all-to-all send buffer ``[G, V, S/G, f, C]`` directly
+        (position-major rows, no pack pass) -> one row permutation into ``[V * S/G, F, C]`` -> temporal transformer
+        -> inverse permutation -> all-to-all -> the residual pass reads the receive buffer in place."""
+        from .fastpath import OWNED_INPUT_FLAG
+
+        bf, C, h, w = hidden_states.shape
+        V, S, G = bf // f, h * w, self.world
+        Sl = S // G
+        norm = module.norm
+        groups = norm.num_groups
+        sums = ops.group_norm_nhwc_sums(hidden_states, groups, f)                         # [V, groups, 2] fp32
+        self._collective("stat_gather", lambda: dist.all_reduce(sums, group=self.group), sums.numel() * 4)
+        self.stats["stat_gathers"] += 1
+        cnt = float(f * G) * float(C // groups) * float(S)
+        mean = sums[..., 0] / cnt
+        rstd = torch.rsqrt((sums[..., 1] / cnt - mean * mean).clamp_min_(0.0) + norm.eps)
+        send = ops.group_norm_nhwc_apply(hidden_states, norm.weight, norm.bias,
+                                         torch.stack([mean, rstd], dim=-1).contiguous(), groups, f, world=G)
+        recv = torch.empty_like(send)                                                     # [G, V, Sl, f, C]
+        nbytes = send.numel() * send.element_size() * (G - 1) / G
+        self._collective("all_to_all", lambda: dist.all_to_all_single(recv, send, group=self.group), nbytes)
+        self.stats["all_to_alls"] += 1
+        t = ops.reshard_unpack(recv.view(G, V * Sl, f, 1, C), G).view(V * Sl, G * f, C)   # every frame, my positions
+        t = module.proj_in(t)
+        for block in module.transformer_blocks:
+            block.__dict__[OWNED_INPUT_FLAG] = True
+            t = block(t, encoder_hidden_states=kw.get("encoder_hidden_states"), timestep=kw.get("timestep"),
+                      cross_attention_kwargs=kw.get("cross_attention_kwargs"), class_labels=kw.get("class_labels"))
+            block.__dict__.pop(OWNED_INPUT_FLAG, None)
+        t = module.proj_out(t)
+        send2 = ops.reshard_unpack(t.view(V * Sl, G * f, 1, C).contiguous(), G, inverse=True)   # [G, V*Sl, f, 1, C]
+        recv2 = torch.empty_like(send2)
+        self._collective("all_to_all", lambda: dist.all_to_all_single(recv2, send2, group=self.group), nbytes)
+        self.stats["all_to_alls"] += 1
+        out = ops.sharded_positions_to_nhwc_residual(recv2, hidden_states, f, G)
         if kw.get("return_dict", True):
             from .hostmodel.i2v_adapter import _Sample
             return _Sample(out)

@@ -195,6 +195,22 @@ int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, voi
  *   in-place-capable per-channel bias add out = y + bias (a convolution bias cuDNN would apply as a separate pass). */
 int i2v_upsample2x_nhwc(const void* x, void* out, int N, int h, int w, int C, void* stream);
 
+/* Frame-sharded motion module (partition.FramePartitioner.temporal_forward; new functionality): the
+ * GroupNorm of TransformerTemporalModel (constructed at src/models/unet_motion_cross_frame_attn.py:232-244) spans all
+ * F frames of a video, of which a rank holds fg = F / W.
+ *   i2v_gn_nhwc_sums   : raw per-(video, group) (sum, sum of squares) of the local frames -> sums [N / fg, G, 2]
+ *                        (the caller all-reduces them over the W ranks and forms mean / rstd);
+ *   i2v_gn_nhwc_apply  : the apply pass of i2v_gn_nhwc with caller-provided (mean, rstd) [N / fg, G, 2]; perm = 2 writes
+ *                        the all-to-all send buffer [W, V, S / W, fg, C] (position-major rows grouped by destination
+ *                        rank) directly;
+ *   i2v_rows_residual_sharded : the way back -- y is the all-to-all receive buffer in that same layout; out = y + res
+ *                        on the channels-last [N, S, C] activation. */
+int i2v_gn_nhwc_sums(const void* x, float* sums, float* scratch, int N, int S, int C, int G, int fg, void* stream);
+int i2v_gn_nhwc_apply(const void* x, const void* add, const void* w, const void* b, void* out, const float* mean_rstd,
+                      int N, int S, int C, int G, int fg, int silu, int perm, int world, void* stream);
+int i2v_rows_residual_sharded(const void* y, const void* res, void* out, int N, int S, int C, int fg, int world,
+                              void* stream);
+
 /* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
  * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),
  * key 3: dense-attention tile variant + 1 for head dims <= 48 (see capi.cu), key 5: 1 = IP-Adapter attention on the

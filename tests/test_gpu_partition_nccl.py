@@ -16,7 +16,7 @@ from test_partition_gloo import _free_port  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-def _nccl_worker(rank, world, port, errq):
+def _nccl_worker(rank, world, port, errq, scenario="default"):
     import traceback
 
     import torch.distributed as dist
@@ -42,11 +42,20 @@ def _nccl_worker(rank, world, port, errq):
         assert torch.equal(positions_to_frames(y), mine)
 
         # 2. frame-sharded UNet (SD1.5 head dims 40/80/160, one layer per block) vs the unsharded forward
+        #    scenario "one_frame_unfused": one frame per rank and separate attn1 / i2v_adapter launches -- the local
+        #    rows of every rank but the owner are NOT frame 0, the K/V must come from the owner's broadcast
         unet = make_unet(SD15_HEADDIM_CFG, ip_adapter=True, dtype=torch.bfloat16, device=dev)
-        F = 4 * world
-        sample, ctx, img = unet_inputs(unet, videos=1, frames=F, size=32, tokens=77, image_embed_dim=64)
+        with torch.no_grad():   # the adapter's zero-initialised output projection would hide the cross-frame branch
+            gen = torch.Generator().manual_seed(9)
+            for name, p in unet.named_parameters():
+                if ".i2v_adapter.to_out.0." in name:
+                    p.copy_((torch.randn(p.shape, generator=gen) * 0.02).to(p))
+        one_frame = scenario == "one_frame_unfused"
+        F = world if one_frame else 4 * world
+        videos = 2 if one_frame else 1
+        sample, ctx, img = unet_inputs(unet, videos=videos, frames=F, size=32, tokens=77, image_embed_dim=64)
         sample, ctx, img = sample.to(dev, torch.bfloat16), ctx.to(dev, torch.bfloat16), img.to(dev, torch.bfloat16)
-        install(unet)
+        install(unet, fuse_cross_frame=not one_frame)
         with torch.no_grad():
             ref = unet(sample, 37, True, ctx, added_cond_kwargs={"image_embeds": img}).sample.float()
         part = FramePartitioner(unet).install()
@@ -69,7 +78,8 @@ def _nccl_worker(rank, world, port, errq):
             dist2.destroy_process_group()
 
 
-def test_frame_sharded_unet_nccl():
+@pytest.mark.parametrize("scenario", ["default", "one_frame_unfused"])
+def test_frame_sharded_unet_nccl(scenario):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 CUDA devices (run with gpurun --gpus 2)")
@@ -78,7 +88,7 @@ def test_frame_sharded_unet_nccl():
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, errq)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, errq, scenario)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
