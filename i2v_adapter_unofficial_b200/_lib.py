@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "i2v_layernorm_pre_fwd",
     "i2v_geglu_ld_fwd",
     "i2v_ff_geglu_fwd",
+    "i2v_linear_fwd",
     "i2v_upsample2x_nhwc",
     "i2v_geglu_fwd",
     "i2v_gn_stats",
@@ -120,6 +121,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.i2v_upsample2x_nhwc.argtypes = [p, p, i, i, i, i, p]
     lib.i2v_ff_geglu_fwd.restype = i
     lib.i2v_ff_geglu_fwd.argtypes = [p, p, p, p, ll, i, i, i, p]
+    lib.i2v_linear_fwd.restype = i
+    lib.i2v_linear_fwd.argtypes = [p, p, p, p, p, ll, i, i, i, i, i, p]
     lib.i2v_gn_stats.restype = i
     lib.i2v_gn_stats.argtypes = [p, p, i, i, i, i, p]
     lib.i2v_gn_apply_transpose.restype = i

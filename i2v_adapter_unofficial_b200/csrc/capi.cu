@@ -16,6 +16,7 @@
 #include "norm_layout.cuh"
 #include "temporal_attn.cuh"
 #include "ff_geglu_gemm_sm100.cuh"
+#include "tok_gemm_sm100.cuh"
 
 namespace {
 
@@ -587,6 +588,19 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   }
   const int emu = g_tuning[2] > 0 ? g_tuning[2] - 1 : -1;
   ProfScope prof(1, seq, batch, (cudaStream_t)stream);
+  // tuning key 7 (this entry): 1 / 2 / 3 = column-split softmax (two threads per row) with 3 / 2 / 4 of 8 pairs emulated
+  if (g_tuning[7] == 1) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, true>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 2) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true, true>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 3) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true, true>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 4) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, true, true>>(P, (cudaStream_t)stream);
+#ifdef I2V_EXPERIMENTS
+  if (g_tuning[7] == 7) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 1>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 8) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true, false, 1>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 9) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true, false, 1>>(P, (cudaStream_t)stream);
+  // hand-off pipeline floor: no exponentials at all (results are garbage), one / two threads per row
+  if (g_tuning[7] == 5) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 0, true>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 6) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 0, true, true>>(P, (cudaStream_t)stream);
+#endif
   switch (emu) {
     case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, true>>(P, (cudaStream_t)stream);
     case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true>>(P, (cudaStream_t)stream);
@@ -855,10 +869,10 @@ int i2v_geglu_ld_fwd(const void* x, void* y, long long rows, int D, int ld_out, 
 }
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix: dims (cols, rows), box (64, 128), 128-byte swizzle.
-static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols, int pitch = 0) {
+static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols, int pitch = 0, int box_rows = 128) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(pitch ? pitch : cols) * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -938,6 +952,102 @@ int i2v_ff_geglu_fwd(const void* x, const void* w, const void* bias, void* y, lo
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// token GEMM (tok_gemm_sm100.cuh)
+// ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+template <int TILE_N>
+static int launch_tok_gemm(i2v::TokGemmParams& P, const void* w, int ncl, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kern = i2v::tok_gemm_kernel<TILE_N>;
+  if (!attr_set[dev & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kTgSmemBytes));
+    attr_set[dev & 63] = true;
+  }
+  int rc = make_tmap_2d(&P.tm_w, w, P.N, P.K, 0, TILE_N / 2);
+  if (rc) return rc;
+  P.n_tiles = (P.N + TILE_N - 1) / TILE_N;
+  const long long units = (long long)P.m_pairs * P.n_tiles;
+  const long long clusters = units < ncl ? units : ncl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cfg.blockDim = dim3(i2v::kTgThreads);
+  cfg.dynamicSmemBytes = i2v::kTgSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  ProfScope prof(4, P.rows, P.N, stream);
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" {
+
+int i2v_linear_fwd(const void* x, const void* w, const void* bias, const void* res, void* out, long long rows, int K,
+                   int N, int ld_x, int ld_res, int ld_out, void* stream) {
+  if (rows <= 0 || K <= 0 || N <= 0) return fail(I2V_ERR_BAD_SHAPE, "linear: sizes must be positive");
+  if (K % 8 || N % 8 || ld_x % 8 || ld_out % 8 || (res && ld_res % 8))
+    return fail(I2V_ERR_MISALIGNED, "linear: K, N and the row pitches must be multiples of 8 elements (K=%d N=%d ld_x=%d ld_out=%d ld_res=%d)",
+                K, N, ld_x, ld_out, ld_res);
+  if (ld_x < K || ld_out < N || (res && ld_res < N)) return fail(I2V_ERR_BAD_SHAPE, "linear: a row pitch is smaller than its row");
+  if (!x || !w || !out) return fail(I2V_ERR_BAD_SHAPE, "linear: null pointer");
+  if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (res && !aligned16(res)))
+    return fail(I2V_ERR_MISALIGNED, "linear: pointers must be 16-byte aligned");
+  if (rows > 0x7fffffffLL - 256) return fail(I2V_ERR_BAD_SHAPE, "linear: too many rows (%lld)", rows);
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if ((rc = get_encode_fn())) return rc;
+  i2v::TokGemmParams P;
+  memset(&P, 0, sizeof(P));
+  if ((rc = make_tmap_2d(&P.tm_x, x, rows, K, ld_x))) return rc;
+  P.bias = (const __nv_bfloat16*)bias; P.res = (const __nv_bfloat16*)res; P.out = (__nv_bfloat16*)out;
+  P.rows = rows; P.N = N; P.K = K; P.ld_out = ld_out; P.ld_res = ld_res;
+  P.m_pairs = (int)((rows + 255) / 256);
+  static int max_clusters[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (max_clusters[dev & 63] == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(i2v::tok_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kTgSmemBytes));
+    cudaLaunchConfig_t probe = {};
+    probe.gridDim = dim3((unsigned)(di->sms / 2 * 2));
+    probe.blockDim = dim3(i2v::kTgThreads);
+    probe.dynamicSmemBytes = i2v::kTgSmemBytes;
+    cudaLaunchAttribute pa[1];
+    pa[0].id = cudaLaunchAttributeClusterDimension;
+    pa[0].val.clusterDim.x = 2; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+    probe.attrs = pa; probe.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, i2v::tok_gemm_kernel<256>, &probe) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    if (n <= 0) return fail(I2V_ERR_CUDA, "linear: the device cannot hold a 2-CTA cluster of the GEMM kernel");
+    max_clusters[dev & 63] = n;
+  }
+  const int ncl = max_clusters[dev & 63] < di->sms / 2 ? max_clusters[dev & 63] : di->sms / 2;
+  // tile width: the candidate that covers N with the least padding (ties: the wider tile); tuning key 6 (this entry)
+  // forces one for experiments
+  static const int cand[5] = {256, 224, 192, 160, 128};
+  int best = 256;
+  long long best_waste = -1;
+  for (int c : cand) {
+    const long long waste = (long long)((N + c - 1) / c) * c - N;
+    if (best_waste < 0 || waste < best_waste) { best = c; best_waste = waste; }
+  }
+  if (g_tuning[6] == 128 || g_tuning[6] == 160 || g_tuning[6] == 192 || g_tuning[6] == 224 || g_tuning[6] == 256) best = g_tuning[6];
+  switch (best) {
+    case 256: return launch_tok_gemm<256>(P, w, ncl, (cudaStream_t)stream);
+    case 224: return launch_tok_gemm<224>(P, w, ncl, (cudaStream_t)stream);
+    case 192: return launch_tok_gemm<192>(P, w, ncl, (cudaStream_t)stream);
+    case 160: return launch_tok_gemm<160>(P, w, ncl, (cudaStream_t)stream);
+    default:  return launch_tok_gemm<128>(P, w, ncl, (cudaStream_t)stream);
+  }
 }
 
 static int check_gn_shape(const char* what, int N, int C, int S, int G, int fg) {

@@ -44,8 +44,10 @@ namespace i2v {
 constexpr uint32_t kParkNs = I2V_PARK_NS;   // suspend-time hint of the producer-side waits
 constexpr int kAugCol = 40;   // augmented layout: head-dim column that carries -max (Q), ones (K, V) and the row sum (O)
 
-template <int DK_, int BLOCK_N_, int NT_, int NSTAGES_, int EMU_, int DEG_ = 3, bool AUG_ = false>
+template <int DK_, int BLOCK_N_, int NT_, int NSTAGES_, int EMU_, int DEG_ = 3, bool AUG_ = false, bool SPLIT_ = false,
+          int PAT_ = 0>
 struct PipeCfg {
+  static constexpr int PAT = PAT_;          // which pairs of every 8 take the FMA-pipe exp2 (softmax_exp_row)
   static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16
   static constexpr int BLOCK_N = BLOCK_N_;  // keys per tile
   static constexpr int NT = NT_;            // query tiles (= softmax warpgroups) per CTA
@@ -53,12 +55,21 @@ struct PipeCfg {
   static constexpr int EMU = EMU_;          // of every 8 column pairs, how many take the FMA-pipe exp2
   static constexpr int DEG = DEG_;
   static constexpr bool AUG = AUG_;         // augmented operand layout (see the header comment)
-  static constexpr int THREADS = (4 * NT + 1 + NT) * 32;   // NT softmax warpgroups, 1 TMA warp, NT MMA warps
+  // SPLIT: two threads per query row -- every tile has two softmax warpgroups, each taking BLOCK_N / 2 of a score
+  // tile's columns (TMEM lanes are bound to warp % 4, so warps w and w + 4 of a tile share a lane quarter).  Twice the
+  // warps per SM sub-partition at half the registers each: the softmax code is latency-bound (issue slots 56 % busy
+  // with three in-order warps per sub-partition), not throughput-bound.
+  static constexpr bool SPLIT = SPLIT_;
+  static constexpr int HALVES = SPLIT ? 2 : 1;
+  static constexpr int SM_WARPS = 4 * NT * HALVES;          // softmax warps
+  static constexpr int THREADS = (SM_WARPS + 1 + NT) * 32;  // softmax warpgroups, 1 TMA warp, NT MMA warps
+  static_assert(!SPLIT || (AUG && BLOCK_N == 64 && DK == 48), "the column-split softmax exists for the augmented d = 40 layout");
   static constexpr int KSTEPS = DK / 16;
   static constexpr int Q_TILE_BYTES = 128 * 128;       // one 64-column swizzle sub-tile (DK <= 64)
   static constexpr int KV_TILE_BYTES = BLOCK_N * 128;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = NT * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + 1024;
+  static constexpr int XCHG_BYTES = SPLIT ? NT * 2 * 128 * 4 : 0;   // SPLIT: per-row maxima the two halves exchange (slow path)
+  static constexpr int SMEM_BYTES = NT * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + XCHG_BYTES + 1024;
   static constexpr int TILE_COLS = BLOCK_N + BLOCK_N / 2 + DK;
   static constexpr int TMEM_S = 0, TMEM_P = BLOCK_N, TMEM_O = BLOCK_N + BLOCK_N / 2;  // offsets within a tile's columns
   static_assert(DK % 16 == 0 && DK <= 64, "pipelined kernel: head dim <= 64");
@@ -72,6 +83,7 @@ struct PipeCfg {
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const __grid_constant__ DenseParams P) {
   constexpr int DK = Cfg::DK, BN = Cfg::BLOCK_N, NS = Cfg::NSTAGES, KSTEPS = Cfg::KSTEPS, NT = Cfg::NT;
+  constexpr int kRowThreads = 128 * Cfg::HALVES;   // threads that take part in a tile's S / P hand-offs
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -90,10 +102,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
   uint64_t* bar_pv_done = bar_p_full + NT;            // [NT]   MMA -> softmax: PV(j) retired (P free, O consistent)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bar_pv_done + NT);
   static_assert((3 + 3 * NS + 4 * NT) * 8 <= Cfg::BAR_BYTES, "barrier area");
+  float* sm_xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [NT][2][128] (SPLIT)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kTmaWarp = 4 * NT, kMmaWarp0 = 4 * NT + 1;
+  constexpr int kTmaWarp = Cfg::SM_WARPS, kMmaWarp0 = Cfg::SM_WARPS + 1;
 
   // Persistent CTA: work item = (problem, batch row, head, query block of NT tiles), q-block fastest so the CTAs that
   // share one (batch, head) K/V run at the same time (L2 reuse).  Every role walks the same item sequence; barrier
@@ -123,8 +136,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
     }
     for (int t = 0; t < NT; ++t) {
       mbar_init(bar_s_full + t, 1);
-      mbar_init(bar_s_free + t, 128);
-      mbar_init(bar_p_full + t, 128);
+      mbar_init(bar_s_free + t, kRowThreads);
+      mbar_init(bar_p_full + t, kRowThreads);
       mbar_init(bar_pv_done + t, 1);
     }
     mbar_fence_init();
@@ -244,6 +257,159 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
         __syncwarp();
       }
       g0 += n_kv;
+    }
+  } else if constexpr (Cfg::SPLIT) {
+    // =========================== softmax + epilogue, two threads per query row ===========================
+    // warp w of the tile's eight: lane quarter w & 3 (fixed by the hardware: TMEM lanes 32 * (warp % 4) ..), column half
+    // w >> 2.  Per KV tile a thread holds 32 scores; the row's other 32 are with its partner (same lane, warp w ^ 4).
+    // The two warps of a row group agree on the fast / slow path through one bar.red.or per KV tile (a named barrier
+    // over their 64 threads that ORs a predicate); only the slow path exchanges the row maxima, through shared memory.
+    constexpr int HB = BN / 2;                    // columns per thread
+    const int t = warp >> 3;
+    const int quarter = warp & 3, half = (warp >> 2) & 1;
+    const int row = quarter * 32 + lane;          // TMEM lane == query row within the tile
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS + lane_addr;
+    const uint32_t tm_s = tm_tile + Cfg::TMEM_S + half * HB, tm_p = tm_tile + Cfg::TMEM_P + half * (HB / 2);
+    const uint32_t tm_o = tm_tile + Cfg::TMEM_O;
+    const uint32_t pair_bar = 1 + t * 4 + quarter;   // named barrier of the two warps of this row group (ids 1..12)
+    float* xchg_mine = sm_xchg + (t * 2 + half) * 128 + row;
+    const float* xchg_other = sm_xchg + (t * 2 + (half ^ 1)) * 128 + row;
+    uint8_t* q_maxcol = sm_q + t * Cfg::Q_TILE_BYTES + row * 128 + ((((kAugCol * 2) >> 4) ^ (row & 7)) << 4) +
+                        ((kAugCol * 2) & 15);
+    uint32_t it0 = 0;   // KV iterations this tile has run before this item
+    for (int x = blockIdx.x; x < n_items; x += gridDim.x) {
+      const Item item = decode(x);
+      if (t >= item.ntiles) continue;
+      const DenseProblem& prob = *item.prob;
+      const int h = item.h, b = item.b, q0 = item.q0;
+      float m_ref = 0.f;        // where the reference max should be (integer, bf16-exact)
+      float m_col = 0.f;        // what the query tile's max column held when the current S tile was computed
+      bool col_stale = false;   // m_ref moved: the max column must be rewritten (half 0 writes, both halves track it)
+
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(bar_s_full + t, (it0 + j) & 1);
+        tc_fence_after();
+        float sv[HB];
+        {
+          uint32_t r[HB];
+          tmem_ld_x32(tm_s, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < HB; ++i) sv[i] = __uint_as_float(r[i]);
+        }
+        float m_col_next = m_col;
+        if (col_stale) {
+          // QK(j) has retired and QK(j+1) is not issued before all 256 s_free arrivals: the window for the rewrite
+          if (half == 0) {
+            *reinterpret_cast<uint16_t*>(q_maxcol) = (uint16_t)(__float_as_uint(-m_ref) >> 16);
+            fence_proxy_async_smem();
+          }
+          m_col_next = m_ref;
+          col_stale = false;
+        }
+        tc_fence_before();
+        mbar_arrive(bar_s_free + t);
+
+        const int valid = P.skv - j * BN - half * HB;   // columns of this half that exist
+        const bool full = P.skv - j * BN >= BN;          // (uniform over the tile)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < HB; i += 4) {
+          mx0 = fmax3(mx0, sv[i + 0], sv[i + 1]);
+          mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+        }
+        float mx = fmaxf(mx0, mx1);
+        const bool slow_local = (j == 0) || (mx + (m_col - m_ref) > kRescaleThreshold) || (m_col != m_ref) || !full;
+        uint32_t pk[HB / 2];
+        if (named_bar_red_or(pair_bar, 64, slow_local)) {
+          // ---- slow path (first tile of an item, a row outgrew its reference, stale max column, ragged tile) ----
+          if (!full) {
+#pragma unroll
+            for (int i = 0; i < HB; ++i)
+              if (i >= valid) sv[i] = -INFINITY;
+            mx0 = mx1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < HB; i += 4) {
+              mx0 = fmax3(mx0, sv[i + 0], sv[i + 1]);
+              mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+            }
+            mx = fmaxf(mx0, mx1);
+          }
+          *xchg_mine = mx;
+          named_bar_sync(pair_bar, 64);
+          mx = fmaxf(mx, *xchg_other) + (m_col - m_ref);   // the row's max relative to m_ref, identical in both halves
+          named_bar_sync(pair_bar, 64);                     // the slot may be rewritten by the next slow step
+          const bool need = (j == 0) || mx > kRescaleThreshold;
+          float alpha = 1.f;
+          if (need) {
+            const float m_int = ceilf(m_ref + mx);
+            const uint32_t mb = __float_as_uint(m_int);
+            const float m_new = __uint_as_float(m_int >= 0.f ? ((mb + 0xFFFFu) & 0xFFFF0000u) : (mb & 0xFFFF0000u));
+            alpha = (j == 0) ? 0.f : ex2_approx(m_ref - m_new);
+            m_ref = m_new;
+            col_stale = true;
+          }
+          if (j > 0 && __any_sync(0xffffffffu, need)) {
+            // O row *= alpha on this half's 24 accumulator columns; PV(j-1) must have retired, PV(j) is not issued
+            // before all p_full arrivals
+            mbar_wait(bar_pv_done + t, (it0 + j - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cch = 0; cch < 3; ++cch) {
+              uint32_t r[8];
+              tmem_ld_x8(tm_o + half * 24 + cch * 8, r);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_x8(tm_o + half * 24 + cch * 8, r);
+            }
+          }
+          const float delta = m_ref - m_col;   // exact: both are small integers
+#pragma unroll
+          for (int i = 0; i < HB; ++i) sv[i] -= delta;
+          softmax_exp_row<HB, 0, 3, true, true, false>(sv, 1.f, 0.f, pk);
+        } else {
+          softmax_exp_row<HB, Cfg::EMU, Cfg::DEG, true, true, false>(sv, 1.f, 0.f, pk);
+        }
+        m_col = m_col_next;
+        if (j > 0) {   // (j == 0: the epilogue of the previous item already waited for its last PV)
+          mbar_wait(bar_pv_done + t, (it0 + j - 1) & 1);   // PV(j-1) has finished reading the P columns
+          tc_fence_after();
+        }
+        tmem_st_x16(tm_p, pk);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p_full + t);
+      }
+
+      // ---- epilogue: O / l -> bf16 -> global; half 0 writes columns 0..23, half 1 columns 24..39 ----
+      mbar_wait(bar_pv_done + t, (it0 + n_kv - 1) & 1);
+      tc_fence_after();
+      it0 += n_kv;
+      const int qrow = q0 + t * 128 + row;
+      __nv_bfloat16* orow = prob.o + (long long)b * prob.o_sb + (long long)qrow * prob.o_ss + (long long)h * prob.o_sh;
+      uint32_t ro[3][8], rl[8];
+#pragma unroll
+      for (int cch = 0; cch < 3; ++cch) tmem_ld_x8(tm_o + half * 24 + cch * 8, ro[cch]);
+      tmem_ld_x8(tm_o + kAugCol, rl);            // columns 40..47: the row sum sits in column 40
+      tc_wait_ld();
+      const float inv_l = 1.f / __uint_as_float(rl[0]);
+      if (qrow < P.sq) {
+#pragma unroll
+        for (int cch = 0; cch < 3; ++cch) {
+          const int col = half * 24 + cch * 8;
+          if (col < P.d) {
+            const uint32_t* r = ro[cch];
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + col) = v;
+          }
+        }
+      }
     }
   } else {
     // =========================== softmax + epilogue warpgroup of tile t ===========================
@@ -402,7 +568,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
             for (int i = 0; i < BN; ++i) sv[i] -= delta;
             softmax_exp_row<BN, 0, 3, true, true, false>(sv, 1.f, 0.f, pk);
           } else {
-            softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, true, true, false>(sv, 1.f, 0.f, pk);
+            softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, true, true, false, Cfg::PAT>(sv, 1.f, 0.f, pk);
           }
         }
         m_col = m_col_next;

@@ -344,6 +344,12 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                :
@@ -527,7 +533,8 @@ __device__ __forceinline__ uint64_t ex2_emu_pair_x(uint64_t x2) {
 // One softmax row step on BN raw scores held in registers: P = 2^(s*c - m) as packed bf16 pairs (pk) + the fp32 row
 // sum.  EMU of every 8 column pairs take the FMA-pipe path; m must be an integer when EMU > 0.
 // PRESCALED: sv already holds x = s*c - m.  SUM = false: the caller gets the row sum elsewhere (ones column of V).
-template <int BN, int EMU, int DEG, bool CLAMP, bool PRESCALED = false, bool SUM = true>
+// PAT = 1: the EMU pairs of every 8 are spread evenly ((i * EMU) % 8 < EMU) instead of taken first.
+template <int BN, int EMU, int DEG, bool CLAMP, bool PRESCALED = false, bool SUM = true, int PAT = 0>
 __device__ __forceinline__ float softmax_exp_row(const float (&sv)[BN], float c, float m, uint32_t (&pk)[BN / 2]) {
   const uint64_t c2 = f2_pack(c, c);
   const uint64_t nm2 = f2_pack(-m, -m);
@@ -537,7 +544,9 @@ __device__ __forceinline__ float softmax_exp_row(const float (&sv)[BN], float c,
   for (int i = 0; i < BN / 2; ++i) {
     const uint64_t s2 = f2_pack(sv[2 * i], sv[2 * i + 1]);
     uint64_t p2;
-    if ((i & 7) < EMU) {
+    if (DEG == 0) {
+      p2 = s2;   // developer experiment (never dispatched by the library): the hand-off pipeline without exponentials
+    } else if (PAT == 0 ? ((i & 7) < EMU) : (((i * EMU) & 7) < EMU)) {
       p2 = PRESCALED ? ex2_emu_pair_x<DEG, CLAMP>(s2) : ex2_emu_pair_int<DEG, CLAMP>(s2, c2, k1);
     } else {
       float x0, x1;
@@ -554,6 +563,22 @@ __device__ __forceinline__ float softmax_exp_row(const float (&sv)[BN], float c,
   return a0 + a1;
 }
 
+// Named barrier over `nthreads` threads that also OR-reduces a predicate: one instruction for "synchronise the two
+// warps that share a row group and tell both whether either of them needs the slow path".
+__device__ __forceinline__ bool named_bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P, Q;\n\t"
+      "setp.ne.u32 Q, %3, 0;\n\t"
+      "bar.red.or.pred P, %1, %2, Q;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -291,6 +291,53 @@ def ff_geglu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]
     return y
 
 
+def linear_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Shapes `linear` takes: CUDA bf16, rows of x contiguous, K and N multiples of 8, 16-byte aligned bases."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.dim() == 2
+            and weight.is_contiguous() and x.shape[-1] == weight.shape[1] and x.shape[-1] % 8 == 0
+            and weight.shape[0] % 8 == 0 and x.stride(-1) == 1 and x.data_ptr() % 16 == 0
+            and weight.data_ptr() % 16 == 0)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear(x, weight, bias) [+ residual]`` on the library's tcgen05 token GEMM (i2v_linear_fwd).
+
+    x [..., K] (the leading axes must flatten to rows with one pitch), weight [N, K] contiguous, bias [N];
+    ``residual`` [..., N] is added in the epilogue (after the product is rounded to bf16, like the reference's separate
+    add); ``out`` may be the residual itself (in-place accumulation into the residual stream)."""
+    dev = _require_cuda(x, weight)
+    K, N = x.shape[-1], weight.shape[0]
+    if not linear_supported(x, weight):
+        raise ValueError(f"linear: unsupported operands x {tuple(x.shape)} {x.dtype} weight {tuple(weight.shape)}")
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8):
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    ld_x = x2.stride(0) if rows > 1 else K
+    if bias is not None and (bias.shape != (N,) or bias.dtype != torch.bfloat16 or not bias.is_contiguous()):
+        raise ValueError("linear: bias must be a contiguous bf16 [N] vector")
+    res2 = None
+    if residual is not None:
+        if residual.dtype != torch.bfloat16 or residual.shape[-1] != N or residual.numel() != rows * N:
+            raise ValueError(f"linear: residual {tuple(residual.shape)} does not match [{rows}, {N}]")
+        res2 = residual.reshape(rows, N)
+        if not res2.is_contiguous():
+            res2 = res2.contiguous()
+    if out is None:
+        o = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=dev)
+    else:
+        o = out
+        if o.dtype != torch.bfloat16 or not o.is_contiguous() or o.numel() != rows * N:
+            raise ValueError("linear: out must be a contiguous bf16 tensor of rows * N elements")
+    lib = _lib.load()
+    with _on_device(dev):
+        _lib.check(lib.i2v_linear_fwd(x2.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+                                      None if res2 is None else res2.data_ptr(), o.data_ptr(), rows, K, N, ld_x, N, N,
+                                      _stream(dev)))
+    return o
+
+
 def ff_geglu_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
     """Shapes the fused kernel takes (K % 64 == 0, N % 128 == 0, bf16, contiguous)."""
     return (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()

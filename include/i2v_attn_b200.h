@@ -195,6 +195,15 @@ int i2v_rows_residual_bias(const void* y, const void* res, const void* bias, voi
  *   in-place-capable per-channel bias add out = y + bias (a convolution bias cuDNN would apply as a separate pass). */
 int i2v_upsample2x_nhwc(const void* x, void* out, int N, int h, int w, int C, void* stream);
 
+/* i2v_linear_fwd: out[r, n] = sum_k x[r, k] W[n, k] (+ bias[n]) (+ res[r, n]) -- `F.linear` with the residual add in
+ *   the epilogue, for the projections around the attention operators that the reference runs as separate nn.Linear
+ *   calls: to_q / to_k / to_v (src/modules/i2v_adapter.py:468-492 through diffusers Attention), to_out + the residual
+ *   add (:494-501, :533), the feed-forward's output Linear + residual (:554-561), the motion module's proj_in / proj_out.
+ *   bf16; x [rows, K] with row pitch ld_x, W [N, K] contiguous (nn.Linear layout), out / res with pitches ld_out /
+ *   ld_res; K, N and the pitches multiples of 8; bias, res may be NULL; res may alias out.  tcgen05 2-SM MMA. */
+int i2v_linear_fwd(const void* x, const void* w, const void* bias, const void* res, void* out, long long rows, int K,
+                   int N, int ld_x, int ld_res, int ld_out, void* stream);
+
 /* Frame-sharded motion module (partition.FramePartitioner.temporal_forward; new functionality): the
  * GroupNorm of TransformerTemporalModel (constructed at src/models/unet_motion_cross_frame_attn.py:232-244) spans all
  * F frames of a video, of which a rank holds fg = F / W.

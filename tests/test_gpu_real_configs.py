@@ -127,9 +127,9 @@ def test_config1_down_block_matches_cpu_oracle():
     # (2) the whole block on the fast path
     handle = install(block)
     fastpath.reset_fallback_counts()
-    with torch.no_grad():
-        out, _ = block(_bf16(x), _bf16(temb), enable_cross_frame_attn=True, encoder_hidden_states=_bf16(ctx),
-                       num_frames=Fr)
+    with torch.no_grad():   # channels-last input, as the UNet's conv_in hands it to its first block
+        out, _ = block(_bf16(x).contiguous(memory_format=torch.channels_last), _bf16(temb),
+                       enable_cross_frame_attn=True, encoder_hidden_states=_bf16(ctx), num_frames=Fr)
     out = out.float().cpu()
     assert fastpath.fallback_counts() == {}
     handle.uninstall()
