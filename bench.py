@@ -497,7 +497,7 @@ class StepRunner:
         self.torch.cuda.empty_cache()
 
 
-def leg_frame_sharded(unet, sched, dev, rank, world, steps=3, warmup=2, frames=32, latent=64):
+def leg_frame_sharded(unet, sched, dev, rank, world, steps=3, warmup=2, frames=32, latent=64, graph=True):
     """C5: one `frames`-frame clip x CFG.  world == 1: unsharded on this GPU (the reference point).  world > 1: frames
     split over the ranks through FramePartitioner (NCCL broadcast / all-to-all / all-gather of statistics)."""
     import torch
@@ -514,13 +514,27 @@ def leg_frame_sharded(unet, sched, dev, rank, world, steps=3, warmup=2, frames=3
     else:
         lat = inp["latents"].clone()
 
-    def body(i):
+    graphed = None
+    if graph:
+        # one captured graph per rank; with world > 1 it contains the NCCL collectives of the frame partitioner
+        from i2v_adapter_unofficial_b200.graph import GraphedDenoiser
+
+        graphed = GraphedDenoiser(unet, sched, lat, inp["prompt"], GUIDANCE, inp["cond"], inp["image"],
+                                  impose_first_frame=part is None or part.owns_first_frame)
+
+    def eager_body(i):
         nonlocal lat
         if part is not None:
             lat = sharded_denoise_step(part, unet, sched, lat, ts[i % len(ts)], inp["prompt"], GUIDANCE, inp["cond"],
                                        inp["image"])
         else:
             lat = denoise_step(unet, sched, lat, ts[i % len(ts)], inp["prompt"], GUIDANCE, inp["cond"], inp["image"])
+
+    def body(i):
+        if graphed is not None:
+            graphed.step(i)
+        else:
+            eager_body(i)
 
     def barrier():
         if world > 1:
@@ -531,7 +545,7 @@ def leg_frame_sharded(unet, sched, dev, rank, world, steps=3, warmup=2, frames=3
         for i in range(warmup):
             body(i)
         barrier()
-        if part is not None:
+        if part is not None and graphed is None:
             part.start_timing()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -542,13 +556,29 @@ def leg_frame_sharded(unet, sched, dev, rank, world, steps=3, warmup=2, frames=3
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        out = dict(n_gpus=world, frames=frames, latent=latent, steps=steps, warmup=warmup, launch="eager",
+        eager_steps = 0
+        if part is not None and graphed is not None:
+            # events cannot bracket the collectives of a replayed graph: their breakdown comes from two eager steps
+            eager_steps = 2
+            eager_body(0)
+            barrier()
+            part.start_timing()
+            for i in range(eager_steps):
+                eager_body(1 + i)
+            barrier()
+        out = dict(n_gpus=world, frames=frames, latent=latent, steps=steps, warmup=warmup,
+                   launch="CUDA graph replay (collectives captured)" if graphed is not None else "eager",
                    ms_per_step=ms.item() / steps, value=steps / (ms.item() / 1e3), unit=UNIT, scaling="strong",
                    parallelism=("unsharded (reference point)" if part is None else
                                 f"frames sharded {frames // world} per rank: frame-0 K/V broadcast, all-to-all re-shard "
                                 f"around each motion module, GroupNorm statistics all-gather"))
         if part is not None:
-            out["collectives"] = part.timing_summary(steps)
+            out["collectives"] = part.timing_summary(eager_steps or steps)
+            if eager_steps:
+                out["collectives"]["how"] = f"{eager_steps} eager steps after the graph-timed region"
+            iso = sum(v["isolated_ms_per_step"] for v in out["collectives"].values() if isinstance(v, dict))
+            out["collectives_isolated_ms_per_step"] = iso
+            out["collectives_share_of_step"] = iso / out["ms_per_step"]
         return out
     finally:
         if part is not None:
@@ -603,12 +633,12 @@ def run_b200(args, rank, world, local_rank, emitter):
         # headline = the frame-sharded clip itself
         emitter.guard("c5", 600)
         res = leg_frame_sharded(unet, sched, dev, rank, world, steps=args.steps, warmup=args.warmup,
-                                frames=wl["frames"], latent=wl["latent"])
+                                frames=wl["frames"], latent=wl["latent"], graph=args.graph)
         emitter.cancel()
         emitter.line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=world, steps=args.steps,
                             warmup=args.warmup, ms_per_step=res["ms_per_step"], higher_is_better=True, scaling="strong",
                             vs_baseline=None, dtype="bf16", data="synthetic",
-                            config=dict(workload=wl["text"], parallelism=res["parallelism"], launch="eager"),
+                            config=dict(workload=wl["text"], parallelism=res["parallelism"], launch=res["launch"]),
                             e2e=None, gpu_launches=int(_lib.launch_count()), collectives=res.get("collectives"),
                             fast_path_fallbacks=fastpath.fallback_counts())
         emitter.emit()
@@ -687,7 +717,7 @@ def run_b200(args, rank, world, local_rank, emitter):
         try:
             emitter.guard("c5", 300)
             legs["c5"] = dict(workload=WORKLOADS["c5"]["text"],
-                              **leg_frame_sharded(unet, sched, dev, rank, world, steps=3, warmup=2))
+                              **leg_frame_sharded(unet, sched, dev, rank, world, steps=3, warmup=2, graph=args.graph))
         except Exception as e:  # noqa: BLE001
             legs["c5"] = dict(error=f"{type(e).__name__}: {e}")
         emitter.cancel()

@@ -588,7 +588,8 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   }
   const int emu = g_tuning[2] > 0 ? g_tuning[2] - 1 : -1;
   ProfScope prof(1, seq, batch, (cudaStream_t)stream);
-  // tuning key 7 (this entry): 1 / 2 / 3 = column-split softmax (two threads per row) with 3 / 2 / 4 of 8 pairs emulated
+  // tuning key 7 (this entry), experiments kept for the record: 1 / 2 / 3 / 4 = column-split softmax (two
+  // threads per row) with 3 / 2 / 4 / 0 of 8 pairs emulated -- measured 14 % slower than the default
   if (g_tuning[7] == 1) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, true>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 2) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true, true>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 3) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true, true>>(P, (cudaStream_t)stream);
@@ -597,6 +598,8 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   if (g_tuning[7] == 7) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 1>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 8) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true, false, 1>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 9) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true, false, 1>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 10) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 2>>(P, (cudaStream_t)stream);   // QK issued twice
+  if (g_tuning[7] == 11) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, true, false, 2>>(P, (cudaStream_t)stream);   // ... with EMU 0
   // hand-off pipeline floor: no exponentials at all (results are garbage), one / two threads per row
   if (g_tuning[7] == 5) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 0, true>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 6) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 0, true, true>>(P, (cudaStream_t)stream);
@@ -869,14 +872,15 @@ int i2v_geglu_ld_fwd(const void* x, void* y, long long rows, int D, int ld_out, 
 }
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix: dims (cols, rows), box (64, 128), 128-byte swizzle.
-static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols, int pitch = 0, int box_rows = 128) {
+static int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols, int pitch = 0, int box_rows = 128,
+                        int box_cols = 64) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(pitch ? pitch : cols) * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(I2V_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) for a [%lld, %d] matrix", (int)r, rows, cols);
   return 0;
@@ -1009,8 +1013,10 @@ int i2v_linear_fwd(const void* x, const void* w, const void* bias, const void* r
   i2v::TokGemmParams P;
   memset(&P, 0, sizeof(P));
   if ((rc = make_tmap_2d(&P.tm_x, x, rows, K, ld_x))) return rc;
-  P.bias = (const __nv_bfloat16*)bias; P.res = (const __nv_bfloat16*)res; P.out = (__nv_bfloat16*)out;
-  P.rows = rows; P.N = N; P.K = K; P.ld_out = ld_out; P.ld_res = ld_res;
+  if ((rc = make_tmap_2d(&P.tm_out, out, rows, N, ld_out, 128, 32))) return rc;
+  if (res && (rc = make_tmap_2d(&P.tm_res, res, rows, N, ld_res, 128, 32))) return rc;
+  P.bias = (const __nv_bfloat16*)bias; P.has_res = res ? 1 : 0;
+  P.rows = rows; P.N = N; P.K = K;
   P.m_pairs = (int)((rows + 255) / 256);
   static int max_clusters[64] = {0};
   int dev = 0;
@@ -1031,14 +1037,17 @@ int i2v_linear_fwd(const void* x, const void* w, const void* bias, const void* r
     max_clusters[dev & 63] = n;
   }
   const int ncl = max_clusters[dev & 63] < di->sms / 2 ? max_clusters[dev & 63] : di->sms / 2;
-  // tile width: the candidate that covers N with the least padding (ties: the wider tile); tuning key 6 (this entry)
-  // forces one for experiments
+  // tile width: fewest "rounds x tile width" over the persistent CTA pairs -- a padded last tile and a partly filled last
+  // round (few row blocks: 8192 rows x N = 1280 is 160 units of 256 columns on 74 pairs, three rounds for two rounds'
+  // worth of work) both cost; ties go to the wider tile.  Tuning key 6 (this entry) forces a width for experiments.
   static const int cand[5] = {256, 224, 192, 160, 128};
   int best = 256;
-  long long best_waste = -1;
+  long long best_cost = -1;
   for (int c : cand) {
-    const long long waste = (long long)((N + c - 1) / c) * c - N;
-    if (best_waste < 0 || waste < best_waste) { best = c; best_waste = waste; }
+    const long long units = (long long)P.m_pairs * ((N + c - 1) / c);
+    const long long rounds = (units + ncl - 1) / ncl;
+    const long long cost = rounds * (c + 24);
+    if (best_cost < 0 || cost < best_cost) { best = c; best_cost = cost; }
   }
   if (g_tuning[6] == 128 || g_tuning[6] == 160 || g_tuning[6] == 192 || g_tuning[6] == 224 || g_tuning[6] == 256) best = g_tuning[6];
   switch (best) {

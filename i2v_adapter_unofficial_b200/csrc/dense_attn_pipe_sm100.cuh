@@ -193,6 +193,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
 
     auto issue_qk = [&](int s) {
       const uint32_t ka = (k_addr + s * Cfg::KV_TILE_BYTES) >> 4;
+#ifdef I2V_EXPERIMENTS
+      // PAT == 2 (developer experiment): every QK^T is issued twice (same result) -- does the run time grow by the
+      // added tensor time (MMA on the critical path) or not (hidden behind the softmax)?
+      if (Cfg::PAT == 2) {
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          const uint64_t da = desc_k_major | (uint64_t)((qa + kk * 2) & 0x3FFF);
+          const uint64_t db = desc_k_major | (uint64_t)((ka + kk * 2) & 0x3FFF);
+          umma_ss(tm_tile + Cfg::TMEM_S, da, db, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      }
+#endif
 #pragma unroll
       for (int kk = 0; kk < KSTEPS; ++kk) {
         const uint64_t da = desc_k_major | (uint64_t)((qa + kk * 2) & 0x3FFF);   // 32 bytes per 16-column k-step

@@ -25,12 +25,17 @@ import torch
 class GraphedDenoiser:
     def __init__(self, unet, scheduler, latents: torch.Tensor, prompt_embeds: torch.Tensor,
                  guidance_scale: float = 7.5, condition_image_latents: Optional[torch.Tensor] = None,
-                 image_embeds: Optional[torch.Tensor] = None, warmup: int = 2, before_capture=None):
+                 image_embeds: Optional[torch.Tensor] = None, warmup: int = 2, before_capture=None,
+                 impose_first_frame: bool = True):
         if not latents.is_cuda:
             raise RuntimeError("GraphedDenoiser captures a CUDA graph: the buffers must live on a CUDA device")
         if scheduler.num_inference_steps is None:
             raise ValueError("call scheduler.set_timesteps(...) first")
         self.unet, self.scheduler, self.guidance_scale = unet, scheduler, float(guidance_scale)
+        # frame shards (partition.FramePartitioner): only the rank that owns global frame 0 re-imposes the condition
+        # latents; the collectives of the sharded forward (NCCL broadcast / all-to-all / all-reduce) are captured
+        # into the graph like any other kernel, every rank capturing the same sequence
+        self.impose_first_frame = bool(impose_first_frame)
         dev = latents.device
         self.latents = latents.clone()
         self.prompt = prompt_embeds.clone()
@@ -82,7 +87,7 @@ class GraphedDenoiser:
         lat = self.latents
         has_condition = self.cond is not None
         do_cfg = self.guidance_scale > 1.0
-        if has_condition:
+        if has_condition and self.impose_first_frame:
             lat[:, 0] = self.cond                                                            # pipeline :668-669
         inp = torch.cat([lat] * 2) if do_cfg else lat                                        # :672
         added = {"image_embeds": self.image} if self.image is not None else None

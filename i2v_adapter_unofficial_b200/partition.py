@@ -195,7 +195,7 @@ class FramePartitioner:
     def start_timing(self) -> None:
         self._timing = {"broadcast": [], "all_to_all": [], "stat_gather": []}
 
-    def _collective(self, kind: str, fn: Callable[[], Any], nbytes: float):
+    def _collective(self, kind: str, fn: Callable[[], Any], nbytes: float, buffer_bytes: int = 0):
         """Run one collective; when timing is on, bracket it with events on the current stream (the NCCL work is
         stream-ordered with it) and remember the bytes this rank moves."""
         if self._timing is None or not torch.cuda.is_available():
@@ -204,21 +204,58 @@ class FramePartitioner:
         e0.record()
         out = fn()
         e1.record()
-        self._timing[kind].append((e0, e1, float(nbytes)))
+        self._timing[kind].append((e0, e1, float(nbytes), int(buffer_bytes)))
         return out
+
+    def _isolated_ms(self, kind: str, buffer_bytes: int, device, reps: int = 5) -> float:
+        """One collective of this kind and size on its own, ranks synchronised, back to back: the NCCL / NVLink time
+        without the skew between ranks that the in-step brackets include."""
+        n = max(buffer_bytes // 2, self.world)
+        n -= n % self.world
+        a = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        b = torch.empty_like(a)
+        if kind == "all_to_all":
+            fn = lambda: dist.all_to_all_single(b, a, group=self.group)  # noqa: E731
+        elif kind == "broadcast":
+            fn = lambda: dist.broadcast(a, src=self.root, group=self.group)  # noqa: E731
+        else:
+            small = torch.zeros(max(buffer_bytes // 4, 1), dtype=torch.float32, device=device)
+            fn = lambda: dist.all_reduce(small, group=self.group)  # noqa: E731
+        for _ in range(2):
+            fn()
+        dist.barrier(group=self.group)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
 
     def timing_summary(self, steps: int) -> Dict[str, Any]:
         """Per step and per kind: calls, device ms inside the collectives (includes waiting for the slowest rank),
         bytes this rank sends, and the resulting GB/s."""
         torch.cuda.synchronize()
         out: Dict[str, Any] = {}
-        for kind, pairs in (self._timing or {}).items():
-            ms = sum(a.elapsed_time(b) for a, b, _ in pairs)
-            nbytes = sum(n for _, _, n in pairs)
-            out[kind] = dict(calls_per_step=len(pairs) / max(steps, 1), ms_per_step=ms / max(steps, 1),
-                             bytes_per_step_per_rank=nbytes / max(steps, 1),
-                             gb_per_s_per_rank=(nbytes / 1e9) / (ms / 1e3) if ms > 0 else None)
-        self._timing = None
+        timing, self._timing = self._timing or {}, None
+        device = torch.device("cuda", torch.cuda.current_device())
+        for kind, pairs in timing.items():
+            ms = sum(a.elapsed_time(b) for a, b, _, _ in pairs)
+            nbytes = sum(n for _, _, n, _ in pairs)
+            # the same collectives on their own (per distinct size, ranks synchronised): what NVLink / NCCL take
+            iso_cache: Dict[int, float] = {}
+            iso = 0.0
+            for _, _, _, buf in pairs:
+                if buf not in iso_cache:
+                    iso_cache[buf] = self._isolated_ms(kind, buf, device)
+                iso += iso_cache[buf]
+            out[kind] = dict(calls_per_step=len(pairs) / max(steps, 1), in_step_ms_per_step=ms / max(steps, 1),
+                             bytes_sent_per_step_per_rank=nbytes / max(steps, 1),
+                             isolated_ms_per_step=iso / max(steps, 1),
+                             isolated_gb_per_s_per_rank=(nbytes / 1e9) / (iso / 1e3) if iso > 0 else None)
+        out["note"] = ("in_step: event brackets around each collective inside eager steps (include waiting for the slowest "
+                       "rank); isolated: the same calls replayed alone with synchronised ranks")
         return out
 
     # -- frame axis helpers ------------------------------------------------------------------------------------
@@ -246,7 +283,7 @@ class FramePartitioner:
         if tuple(t.shape) != tuple(shape):
             raise ValueError(f"first-frame tensor has shape {tuple(t.shape)}, expected {tuple(shape)}")
         self._collective("broadcast", lambda: dist.broadcast(t, src=self.root, group=self.group),
-                         t.numel() * t.element_size() if self.owns_first_frame else 0)
+                         t.numel() * t.element_size() if self.owns_first_frame else 0, t.numel() * t.element_size())
         self.stats["broadcasts"] += 1
         return t
 
@@ -302,7 +339,7 @@ class FramePartitioner:
         norm = module.norm
         groups = norm.num_groups
         sums = ops.group_norm_nhwc_sums(hidden_states, groups, f)                         # [V, groups, 2] fp32
-        self._collective("stat_gather", lambda: dist.all_reduce(sums, group=self.group), sums.numel() * 4)
+        self._collective("stat_gather", lambda: dist.all_reduce(sums, group=self.group), sums.numel() * 4, sums.numel() * 4)
         self.stats["stat_gathers"] += 1
         cnt = float(f * G) * float(C // groups) * float(S)
         mean = sums[..., 0] / cnt
@@ -311,7 +348,8 @@ class FramePartitioner:
                                          torch.stack([mean, rstd], dim=-1).contiguous(), groups, f, world=G)
         recv = torch.empty_like(send)                                                     # [G, V, Sl, f, C]
         nbytes = send.numel() * send.element_size() * (G - 1) / G
-        self._collective("all_to_all", lambda: dist.all_to_all_single(recv, send, group=self.group), nbytes)
+        self._collective("all_to_all", lambda: dist.all_to_all_single(recv, send, group=self.group), nbytes,
+                         send.numel() * send.element_size())
         self.stats["all_to_alls"] += 1
         t = ops.reshard_unpack(recv.view(G, V * Sl, f, 1, C), G).view(V * Sl, G * f, C)   # every frame, my positions
         t = module.proj_in(t)
@@ -323,7 +361,8 @@ class FramePartitioner:
         t = module.proj_out(t)
         send2 = ops.reshard_unpack(t.view(V * Sl, G * f, 1, C).contiguous(), G, inverse=True)   # [G, V*Sl, f, 1, C]
         recv2 = torch.empty_like(send2)
-        self._collective("all_to_all", lambda: dist.all_to_all_single(recv2, send2, group=self.group), nbytes)
+        self._collective("all_to_all", lambda: dist.all_to_all_single(recv2, send2, group=self.group), nbytes,
+                         send2.numel() * send2.element_size())
         self.stats["all_to_alls"] += 1
         out = ops.sharded_positions_to_nhwc_residual(recv2, hidden_states, f, G)
         if kw.get("return_dict", True):

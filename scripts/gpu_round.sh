@@ -28,10 +28,12 @@ ncu_ff)
 launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-legs --no-e2e --eager --profiler-range > gpurun_out/bench_under_ncu.log 2>&1 ;;
 sanitizer)
-  ( timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "not full_size" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitizer_memcheck.log )
-  tail -5 gpurun_out/sanitizer_memcheck.log
-  ( timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "augmented_layout_matches or temporal_matches or ip_" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/sanitizer_racecheck.log )
-  tail -5 gpurun_out/sanitizer_racecheck.log ;;
+  ( timeout 900 compute-sanitizer --tool memcheck --error-exitcode 1 python scripts/sanitize_small.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitizer_memcheck.log )
+  tail -6 gpurun_out/sanitizer_memcheck.log
+  ( timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 python scripts/sanitize_small.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/sanitizer_racecheck.log )
+  tail -6 gpurun_out/sanitizer_racecheck.log
+  ( timeout 900 compute-sanitizer --tool synccheck --error-exitcode 1 python scripts/sanitize_small.py > gpurun_out/sanitizer_synccheck.log 2>&1; echo "synccheck exit $?" >> gpurun_out/sanitizer_synccheck.log )
+  tail -4 gpurun_out/sanitizer_synccheck.log ;;
 *) echo "unknown part $part" ;;
 esac
 done

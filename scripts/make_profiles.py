@@ -76,6 +76,7 @@ def main():
                 "| ms | share | launches | kernel |\n|---:|---:|---:|---|\n")
         for k, v in tot.most_common(40):
             f.write(f"| {v:.3f} | {v / T * 100:.1f} % | {cnt[k]} | `{k[:150]}` |\n")
+    t_rep = os.path.join(SRC, "prof_temporal.ncu-rep")
     d_txt, d = ncu_digest(os.path.join(SRC, "prof_dense.ncu-rep"), f"Dense attention kernel, level 0 ({TAG})",
                           "Fused spatial self-attention + I2V-Adapter cross-frame attention of one level-0 block at the C2 size "
                           "(32 frames x 8 heads x S=4096 x d=40, two problems, 1.374 TFLOP algorithmic per launch) on the "
@@ -83,7 +84,7 @@ def main():
                           "exponential-bound (MUFU.EX2 16/clk/SM -> 1024 clk per 128x128 score tile vs 384 clk of MMA; 3 of 8 "
                           "column pairs on the FMA-pipe polynomial) -> XU and FMA pipes both busy, tensor pipe ~30 %, "
                           "DRAM << peak (K/V re-reads served by L2).")
-    t_txt, t = ncu_digest(os.path.join(SRC, "prof_temporal.ncu-rep"), f"Temporal attention kernel, level 0 ({TAG})",
+    t_txt, t = (None, {}) if not os.path.exists(t_rep) else ncu_digest(t_rep, f"Temporal attention kernel, level 0 ({TAG})",
                           "Motion-module temporal self-attention at the C2 level-0 size (8192 positions x 16 frames x 8 heads x "
                           "d=40, 335.5 MB algorithmic bytes per launch), launched by `scripts/gpu_selftest.py --run perftemporal`.  "
                           "Expected before measuring: HBM-bound, DRAM traffic ~ algorithmic bytes, tensor/ALU pipes mostly idle.")
@@ -107,13 +108,15 @@ def main():
                                "(TMEM -> GELU -> staged TMA store) not fully hidden at K = 320.")
         open(os.path.join(OUT, f"{TAG}_ff_geglu_gemm_l0.md"), "w").write(f_txt)
         print("ff:", ff.get("gpu__time_duration.sum"), "dram r/w", ff.get("dram__bytes_read.sum"), ff.get("dram__bytes_write.sum"))
-    n8 = os.path.join(SRC, "bench_n8.log")
-    if os.path.exists(n8):
-        line = open(n8).read().strip().splitlines()[-1]
-        json.loads(line)
-        open(os.path.join(OUT, f"{TAG}_bench_n8.json"), "w").write(line + "\n")
     open(os.path.join(OUT, f"{TAG}_dense_attn_l0.md"), "w").write(d_txt)
-    open(os.path.join(OUT, f"{TAG}_temporal_attn_l0.md"), "w").write(t_txt)
+    if t_txt:
+        open(os.path.join(OUT, f"{TAG}_temporal_attn_l0.md"), "w").write(t_txt)
+    for n in (2, 4, 8):
+        path = os.path.join(SRC, f"bench_n{n}.log")
+        if os.path.exists(path):
+            line = open(path).read().strip().splitlines()[-1]
+            json.loads(line)
+            open(os.path.join(OUT, f"{TAG}_bench_n{n}.json"), "w").write(line + "\n")
     bench = open(os.path.join(SRC, "bench.log")).read().strip().splitlines()[-1]
     json.loads(bench)
     open(os.path.join(OUT, f"{TAG}_bench_n1.json"), "w").write(bench + "\n")
