@@ -217,7 +217,8 @@ int launch_dense_pipe_cfg(const i2v::DenseParams& Pin, cudaStream_t stream) {
   DeviceInfo* di = nullptr;
   int rc = device_info(&di);
   if (rc) return rc;
-  const long long grid = items < di->sms ? items : di->sms;   // persistent: one CTA per SM walks the items
+  const long long slots = (long long)di->sms * Cfg::MINB;
+  const long long grid = items < slots ? items : slots;   // persistent: one CTA per SM (or MINB) walks the items
   kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -566,7 +567,11 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   DeviceInfo* di = nullptr;
   if ((rc = device_info(&di))) return rc;
   if ((rc = get_encode_fn())) return rc;
+#ifdef I2V_EXPERIMENTS
+  const int bn = (g_tuning[7] == 14 || g_tuning[7] == 15) ? 48 : 64;
+#else
   const int bn = 64;
+#endif
   i2v::DenseParams P;
   memset(&P, 0, sizeof(P));
   P.nprob = 2;
@@ -600,6 +605,11 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   if (g_tuning[7] == 9) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true, false, 1>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 10) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 2>>(P, (cudaStream_t)stream);   // QK issued twice
   if (g_tuning[7] == 11) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, true, false, 2>>(P, (cudaStream_t)stream);   // ... with EMU 0
+  if (g_tuning[7] == 12) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 8, 3, 3, true>>(P, (cudaStream_t)stream);   // 8-stage K/V ring
+  if (g_tuning[7] == 13) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 3, 3, 3, true>>(P, (cudaStream_t)stream);   // 3-stage K/V ring
+  // one query tile (48-key KV tiles, 120 TMEM columns) per CTA, four / three co-resident CTAs per SM: independent pipelines
+  if (g_tuning[7] == 14) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 1, 3, 3, 3, true, false, 0, 4>>(P, (cudaStream_t)stream);
+  if (g_tuning[7] == 15) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 48, 1, 4, 3, 3, true, false, 0, 3>>(P, (cudaStream_t)stream);
   // hand-off pipeline floor: no exponentials at all (results are garbage), one / two threads per row
   if (g_tuning[7] == 5) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 0, true>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 6) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 0, true, true>>(P, (cudaStream_t)stream);

@@ -45,9 +45,10 @@ constexpr uint32_t kParkNs = I2V_PARK_NS;   // suspend-time hint of the producer
 constexpr int kAugCol = 40;   // augmented layout: head-dim column that carries -max (Q), ones (K, V) and the row sum (O)
 
 template <int DK_, int BLOCK_N_, int NT_, int NSTAGES_, int EMU_, int DEG_ = 3, bool AUG_ = false, bool SPLIT_ = false,
-          int PAT_ = 0>
+          int PAT_ = 0, int MINB_ = 1>
 struct PipeCfg {
   static constexpr int PAT = PAT_;          // which pairs of every 8 take the FMA-pipe exp2 (softmax_exp_row)
+  static constexpr int MINB = MINB_;        // co-resident CTAs per SM (experiment: one query tile per CTA, 3-4 CTAs per SM)
   static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16
   static constexpr int BLOCK_N = BLOCK_N_;  // keys per tile
   static constexpr int NT = NT_;            // query tiles (= softmax warpgroups) per CTA
@@ -74,14 +75,15 @@ struct PipeCfg {
   static constexpr int TMEM_S = 0, TMEM_P = BLOCK_N, TMEM_O = BLOCK_N + BLOCK_N / 2;  // offsets within a tile's columns
   static_assert(DK % 16 == 0 && DK <= 64, "pipelined kernel: head dim <= 64");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 128, "BLOCK_N");
-  static_assert(NT * TILE_COLS <= 512, "TMEM budget");
-  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+  static constexpr int TMEM_COLS = NT * TILE_COLS <= 128 ? 128 : NT * TILE_COLS <= 256 ? 256 : 512;   // allocation: power of two
+  static_assert(NT * TILE_COLS <= 512 && MINB * TMEM_COLS <= 512, "TMEM budget");
+  static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "smem budget");
   static_assert(KV_TILE_BYTES % 1024 == 0, "K/V tiles must keep the 1024-byte swizzle-atom alignment");
   static_assert(THREADS <= 1024, "CTA size");
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const __grid_constant__ DenseParams P) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kernel(const __grid_constant__ DenseParams P) {
   constexpr int DK = Cfg::DK, BN = Cfg::BLOCK_N, NS = Cfg::NSTAGES, KSTEPS = Cfg::KSTEPS, NT = Cfg::NT;
   constexpr int kRowThreads = 128 * Cfg::HALVES;   // threads that take part in a tile's S / P hand-offs
 
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
     }
     mbar_fence_init();
   }
-  if (warp == kMmaWarp0) tmem_alloc<512>(tmem_base_slot);
+  if (warp == kMmaWarp0) tmem_alloc<Cfg::TMEM_COLS>(tmem_base_slot);
   if (warp == kTmaWarp && lane == 0) {
     for (int i = 0; i < P.nprob; ++i) {
       tma_prefetch_desc(&P.prob[i].tm_q);
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) dense_attn_pipe_kernel(const 
   __syncthreads();
   if (warp == kMmaWarp0) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-N=${1:-2}
-( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.log 2> gpurun_out/bench_n$N.err; echo "exit $?" >> gpurun_out/bench_n$N.err )
-tail -c 2500 gpurun_out/bench_n$N.log; tail -8 gpurun_out/bench_n$N.err
+echo "== 7=0 default; 12 / 13 = 8- / 3-stage K/V ring; 14 / 15 = one query tile per CTA (48-key tiles), 4 / 3 CTAs per SM" > gpurun_out/sweep6.log
+I2V_ATTN_LIB=build/lib_exp.so timeout 300 python scripts/perf_dense_sweep.py 7=0 7=12 7=13 7=14 7=15 >> gpurun_out/sweep6.log 2>&1
+cat gpurun_out/sweep6.log
