@@ -578,6 +578,10 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   P.batch = batch; P.heads = heads; P.sq = seq; P.skv = seq; P.d = d;
   P.scale_log2e = 1.f;
   P.seg_split = -1;
+#ifdef I2V_TRACE
+  P.trace = g_trace;
+  P.trace_cta = g_trace_cta;
+#endif
   const DenseSeg segs[2] = {{q_self, k_self, v_self, o_self, 1}, {q_x, k_x, v_x, o_x, num_frames}};
   for (int i = 0; i < 2; ++i) {
     const DenseSeg& s = segs[i];

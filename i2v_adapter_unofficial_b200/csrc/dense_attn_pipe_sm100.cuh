@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
     // Per KV tile j of its query tile: QK(j+1) as soon as K(j+1) has landed and S(j) has been read out, then PV(j) once
     // V(j) has landed and P(j) is stored.  The waits park the warp in hardware.
     const int t = warp - kMmaWarp0;
+    I2V_TRACE_DECL
+    I2V_TRACE_INIT(8 + t)
     constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, DK, 0, 1);
     const uint32_t qa = smem_u32(sm_q + t * Cfg::Q_TILE_BYTES) >> 4;
@@ -233,14 +235,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
         // QK(jj): needs the query tiles (jj == 0), K(jj), and the S columns read out by the softmax warps
         auto qk_step = [&](int jj) {
           const uint32_t g = g0 + jj, itg = it0 + jj;
+          I2V_TRACE_EV(0x10)
           mbar_wait_parked(bar_k_full + g % NS, (g / NS) & 1, kParkNs);
+          I2V_TRACE_EV(0x11)
           if (itg > 0) mbar_wait_parked(bar_s_free + t, (itg - 1) & 1, kParkNs);
           tc_fence_after();
+          I2V_TRACE_EV(0x12)
           if (elect_one()) {
             issue_qk(g % NS);
             tc_commit(bar_s_full + t);
           }
           __syncwarp();
+          I2V_TRACE_EV(0x13)
         };
         mbar_wait_parked(bar_q_full, n & 1, kParkNs);
         qk_step(0);
@@ -249,8 +255,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
           const uint32_t g = g0 + j, itg = it0 + j;
           const int s = g % NS;
           mbar_wait_parked(bar_v_full + s, (g / NS) & 1, kParkNs);
+          I2V_TRACE_EV(0x14)
           mbar_wait_parked(bar_p_full + t, itg & 1, kParkNs);
           tc_fence_after();
+          I2V_TRACE_EV(0x15)
           if (elect_one()) {
             issue_pv(s, j > 0);
             tc_commit(bar_pv_done + t);
@@ -428,6 +436,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
   } else {
     // =========================== softmax + epilogue warpgroup of tile t ===========================
     const int t = warp >> 2;
+    I2V_TRACE_DECL
+    if ((warp & 3) == 0) { I2V_TRACE_INIT(t) }
+    else if ((warp & 3) == 3) { I2V_TRACE_INIT(4 + t) }   // the tile's warp on another sub-partition: skew between them
     const int row = (warp & 3) * 32 + lane;      // TMEM lane == query row within the tile
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS + lane_addr;
@@ -497,6 +508,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
           mbar_wait(bar_pv_done + t, (it0 + j - 1) & 1);   // PV(j-1) has finished reading the P columns
           tc_fence_after();
         }
+        I2V_TRACE_EV(0x6)
         constexpr int H = BN / 2, N16 = H / 16, R8 = (H % 16) / 8;
 #pragma unroll
         for (int cch = 0; cch < N16; ++cch) {
@@ -517,10 +529,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
       };
 
       for (int j = 0; j < n_kv; ++j) {
+        I2V_TRACE_EV(0x1)
         mbar_wait(bar_s_full + t, (it0 + j) & 1);
         tc_fence_after();
+        I2V_TRACE_EV(0x2)
         float sv[BN];
         load_scores(sv);
+        I2V_TRACE_EV(0x3)
         float m_col_next = m_col;
         if (Cfg::AUG && col_stale) {
           // QK(j) has retired (we hold its result) and QK(j+1) is not issued before our s_free arrival: the only
@@ -541,6 +556,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
             if (i >= valid) sv[i] = -INFINITY;
         }
         uint32_t pk[BN / 2];
+        I2V_TRACE_EV(0x4)
         if (!Cfg::AUG) {
           const float mx = row_max(sv) * c;
           // lazy rescale: the reference max only moves when a row outgrows it by more than 2^kRescaleThreshold
@@ -586,7 +602,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
           }
         }
         m_col = m_col_next;
+        I2V_TRACE_EV(0x5)
         store_p(j, pk);
+        I2V_TRACE_EV(0x7)
       }
 
       // ---- epilogue: O / l -> bf16 -> global ----
