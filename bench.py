@@ -64,8 +64,8 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, copied from the committed `ncu --set full` digests (a bench
 # run cannot read hardware counters); the source file is named next to the number in the JSON line
 TRAFFIC = {
-    "dense_l0_c2": (601.9e6, "profiles/r01_dense_attn_l0.md"),
-    "temporal_l0_c2": (312.7e6, "profiles/r01_temporal_attn_l0.md"),
+    "dense_l0_c2": (596.6e6, "profiles/r02_dense_attn_l0.md"),
+    "temporal_l0_c2": (313.1e6, "profiles/r02_temporal_attn_l0.md"),
 }
 
 

@@ -23,16 +23,22 @@ SHAPES = [  # (rows, K, N, bias, residual, what)
 
 
 def timeit(fn, n=20):
+    """GPU time per call: the launches are queued behind a spin kernel, so host-side launch cost (tensor-map encoding
+    through ctypes for the own kernel, cuBLAS heuristics for F.linear) is not in the bracket -- as in a replayed graph."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    ms = []
-    for _ in range(n):
+    best = []
+    for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
+        torch.cuda._sleep(4_000_000)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
         torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1))
-    return statistics.median(ms)
+        best.append(e0.elapsed_time(e1) / n)
+    return statistics.median(best)
 
 
 tot_a = tot_b = 0.0
