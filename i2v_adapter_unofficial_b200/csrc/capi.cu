@@ -12,6 +12,7 @@
 #include "dense_attn_sm100.cuh"
 #include "dense_attn_pipe_sm100.cuh"
 #include "ip_xattn_stream.cuh"
+#include "ip_xattn_tc_sm100.cuh"
 #include "generic_attn.cuh"
 #include "norm_layout.cuh"
 #include "temporal_attn.cuh"
@@ -658,6 +659,44 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
                          q->stride_s % 8 == 0 && k_txt->stride_s % 8 == 0 && v_txt->stride_s % 8 == 0 &&
                          o->stride_s % 8 == 0 && q->stride_b % 8 == 0 && k_txt->stride_b % 8 == 0 &&
                          v_txt->stride_b % 8 == 0 && o->stride_b % 8 == 0;
+    // d = 40 with the pipeline's token counts: tcgen05 kernel with K / V of one (video, head) resident per CTA
+    // (ip_xattn_tc_sm100.cuh); tuning key 5 = 4 keeps the streaming kernel
+    if (d == 40 && n_txt == 77 && n_ip == 4 && (batch / kv_group) * heads <= di->sms && g_tuning[5] == 0) {
+      if ((rc = check_tensor("q", q, 2, true)) || (rc = check_tensor("k", k_txt, 2, true)) ||
+          (rc = check_tensor("v", v_txt, 2, true)) || (rc = check_tensor("k_ip", k_ip, 2, true)) ||
+          (rc = check_tensor("v_ip", v_ip, 2, true)) || (rc = check_tensor("o", o, 2, true)))
+        return rc;
+      if ((rc = get_encode_fn())) return rc;
+      i2v::IpTcParams T;
+      memset(&T, 0, sizeof(T));
+      const int bk = batch / kv_group;
+      if ((rc = make_tmap(&T.tm_q, q, batch, sq, heads, d, 128))) return rc;
+      if ((rc = make_tmap(&T.tm_kt, k_txt, bk, n_txt, heads, d, i2v::kIpTcTxtRows))) return rc;
+      if ((rc = make_tmap(&T.tm_vt, v_txt, bk, n_txt, heads, d, i2v::kIpTcTxtRows))) return rc;
+      if ((rc = make_tmap(&T.tm_ki, k_ip, bk, n_ip, heads, d, 16))) return rc;
+      if ((rc = make_tmap(&T.tm_vi, v_ip, bk, n_ip, heads, d, 16))) return rc;
+      T.o = reinterpret_cast<__nv_bfloat16*>(o->data);
+      T.o_sb = o->stride_b; T.o_ss = o->stride_s; T.o_sh = o->stride_h;
+      T.batch = batch; T.sq = sq; T.heads = heads; T.kv_group = kv_group; T.q_tiles = (sq + 127) / 128;
+      T.scale_log2e = scale * 1.4426950408889634f; T.ip_scale = ip_scale;
+      static bool attr_set[64] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      auto kern = i2v::ip_xattn_tc_kernel<77, 4>;
+      if (!attr_set[dev & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, i2v::kIpTcSmemBytes));
+        attr_set[dev & 63] = true;
+      }
+      const int groups = bk * heads;
+      const long long items = (long long)kv_group * T.q_tiles;
+      int cpg = di->sms / groups;                      // CTAs per (video, head) group
+      if (cpg > items) cpg = (int)items;
+      ProfScope prof(3, sq, batch, (cudaStream_t)stream);
+      kern<<<(unsigned)(groups * cpg), i2v::kIpTcThreads, i2v::kIpTcSmemBytes, (cudaStream_t)stream>>>(T);
+      CUDA_TRY(cudaGetLastError());
+      g_launches.fetch_add(1);
+      return 0;
+    }
     if (hg && heads % hg == 0 && n_txt + n_ip <= i2v::kIpKeys && rows_ok && g_tuning[5] != 1) {
       if ((rc = check_tensor("q", q, 2, true)) || (rc = check_tensor("k", k_txt, 2, true)) ||
           (rc = check_tensor("v", v_txt, 2, true)) || (rc = check_tensor("o", o, 2, true)))
