@@ -133,3 +133,44 @@ def test_load_state_dict_after_install_invalidates_caches():
     before = processors._CACHE_EPOCH[0]
     unet.load_state_dict(unet.state_dict())
     assert processors._CACHE_EPOCH[0] > before
+
+
+def test_fast_path_fallbacks_are_counted():
+    """A swapped forward that cannot take its fast path (here: CPU tensors) hands the call to the stock forward and
+    says so in `fastpath.fallback_counts()`; bench.py asserts the dictionary stays empty on the measured path."""
+    from i2v_adapter_unofficial_b200 import fastpath
+    from i2v_adapter_unofficial_b200.hostmodel.layers import Downsample2D, ResnetBlock2D
+
+    fastpath.reset_fallback_counts()
+    res = ResnetBlock2D(in_channels=32, out_channels=32, temb_channels=64, groups=8).eval()
+    down = Downsample2D(32, padding=0).eval()
+    undo = fastpath.install_fast_forwards(torch.nn.ModuleList([res, down]))
+    x, temb = torch.randn(2, 32, 8, 8), torch.randn(2, 64)
+    with torch.no_grad():
+        y = res(x, temb)
+        z = down(x)
+    assert y.shape == x.shape and z.shape == (2, 32, 4, 4)      # padding = 0 pads right / bottom first (diffusers)
+    counts = fastpath.fallback_counts()
+    assert counts.get("resnet") == 1 and counts.get("downsample") == 1
+    for fn in undo:
+        fn()
+    fastpath.reset_fallback_counts()
+    assert fastpath.fallback_counts() == {}
+
+
+def test_host_attention_takes_a_per_batch_mask():
+    """diffusers' prepare_attention_mask: a (B, 1, L) additive mask is repeated per head."""
+    from i2v_adapter_unofficial_b200.hostmodel.attention import Attention
+
+    torch.manual_seed(0)
+    attn = Attention(64, heads=4, dim_head=16).eval()
+    x = torch.randn(2, 5, 64)
+    mask = torch.zeros(2, 1, 5)
+    mask[:, :, 3:] = -1e4
+    with torch.no_grad():
+        masked = attn(x, attention_mask=mask)
+        ref = attn(x[:, :3], encoder_hidden_states=None)      # the same as dropping the masked keys ... for the kept rows
+        full = attn(x, encoder_hidden_states=x[:, :3])
+    assert masked.shape == (2, 5, 64)
+    assert torch.allclose(masked, full, atol=1e-5)
+    assert torch.allclose(masked[:, :3], ref, atol=1e-5)
