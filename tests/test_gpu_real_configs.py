@@ -282,3 +282,39 @@ def test_library_launch_timing_brackets_the_kernel():
         ms = _lib.prof_read(_lib.PROF_DENSE)
         assert len(ms) == 2 and all(0.0 < m < 50.0 for m in ms), ms
     assert torch.isfinite(o2.float()).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# IP-Adapter attention on the tcgen05 kernel (d = 40, 77 + 4 tokens)
+# ---------------------------------------------------------------------------------------------------------------
+def _ip_ref(q, k, v, nt, ip_scale, g):
+    t = lambda x: x.permute(0, 2, 1, 3).float()  # noqa: E731
+    rep = lambda x: t(x).repeat_interleave(g, 0)  # noqa: E731
+    a = F.scaled_dot_product_attention(t(q), rep(k[:, :nt]), rep(v[:, :nt]))
+    b = F.scaled_dot_product_attention(t(q), rep(k[:, nt:]), rep(v[:, nt:]))
+    return (a + ip_scale * b).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("case", [(32, 4096, 8, 16, 1.0), (2, 77, 8, 1, 0.5), (6, 129, 2, 3, 2.0), (160, 128, 8, 1, 1.0)],
+                         ids=["c2_level0", "one_ragged_tile", "two_heads_three_frames", "more_groups_than_sms"])
+def test_ip_adapter_tcgen05_kernel(case):
+    """`i2v_ip_xattn_fwd` at d = 40 with the pipeline's 77 + 4 tokens: the tcgen05 kernel with K / V resident per (video,
+    head) at the full configs[1] level-0 size, on ragged / tiny query tiles, and the dispatch back to the streaming kernel
+    when there are more (video, head) groups than SMs -- against torch SDPA in fp32 and against the streaming kernel."""
+    B, S, H, g, ip_scale = case
+    d, nt, ni = 40, 77, 4
+    gen = torch.Generator(device=DEV).manual_seed(B + S)
+    q = (torch.randn(B, S, H, d, device=DEV, generator=gen) * 1.5).to(torch.bfloat16)
+    k = (torch.randn(B // g, nt + ni, H, d, device=DEV, generator=gen) * 1.5).to(torch.bfloat16)
+    v = (torch.randn(B // g, nt + ni, H, d, device=DEV, generator=gen) * 3.0).to(torch.bfloat16)   # ones columns vs large V
+    o = ops.ip_xattn(q, k, v, nt, ip_scale, g, None, ops.MODE_FAST)
+    ref = _ip_ref(q, k, v, nt, ip_scale, g)
+    scale = max(1.0, ref.abs().max().item())
+    assert (o.float() - ref).abs().max().item() <= BF16_TOL * scale
+    lib = _lib.load()
+    lib.i2v_set_tuning(5, 4)      # the streaming kernel on the same operands
+    try:
+        o2 = ops.ip_xattn(q, k, v, nt, ip_scale, g, None, ops.MODE_FAST)
+    finally:
+        lib.i2v_set_tuning(5, 0)
+    assert (o.float() - o2.float()).abs().max().item() <= BF16_TOL * scale
