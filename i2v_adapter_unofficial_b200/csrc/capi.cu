@@ -670,7 +670,8 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
       i2v::IpTcParams T;
       memset(&T, 0, sizeof(T));
       const int bk = batch / kv_group;
-      if ((rc = make_tmap(&T.tm_q, q, batch, sq, heads, d, 128))) return rc;
+      T.q = reinterpret_cast<const __nv_bfloat16*>(q->data);
+      T.q_sb = q->stride_b; T.q_ss = q->stride_s; T.q_sh = q->stride_h;
       if ((rc = make_tmap(&T.tm_kt, k_txt, bk, n_txt, heads, d, i2v::kIpTcTxtRows))) return rc;
       if ((rc = make_tmap(&T.tm_vt, v_txt, bk, n_txt, heads, d, i2v::kIpTcTxtRows))) return rc;
       if ((rc = make_tmap(&T.tm_ki, k_ip, bk, n_ip, heads, d, 16))) return rc;
@@ -679,6 +680,10 @@ int i2v_ip_xattn_fwd(const i2v_tensor* q, const i2v_tensor* k_txt, const i2v_ten
       T.o_sb = o->stride_b; T.o_ss = o->stride_s; T.o_sh = o->stride_h;
       T.batch = batch; T.sq = sq; T.heads = heads; T.kv_group = kv_group; T.q_tiles = (sq + 127) / 128;
       T.scale_log2e = scale * 1.4426950408889634f; T.ip_scale = ip_scale;
+#ifdef I2V_TRACE
+      T.trace = g_trace;
+      T.trace_cta = g_trace_cta;
+#endif
       static bool attr_set[64] = {false};
       int dev = 0;
       cudaGetDevice(&dev);
