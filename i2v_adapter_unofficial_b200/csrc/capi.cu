@@ -23,7 +23,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_tuning[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 constexpr int kGnMaxChunks = 64;   // row chunks per image of the channels-last GroupNorm statistics pass
 #ifdef I2V_TRACE
 unsigned long long* g_trace = nullptr;
@@ -468,7 +468,7 @@ int i2v_debug_set_trace(void* device_buffer, int cta) {
 #endif
 
 int i2v_set_tuning(int key, int value) {
-  if (key < 0 || key >= 8) return fail(I2V_ERR_BAD_SHAPE, "unknown tuning key %d", key);
+  if (key < 0 || key >= 12) return fail(I2V_ERR_BAD_SHAPE, "unknown tuning key %d", key);
   g_tuning[key] = value;
   return 0;
 }
@@ -1263,10 +1263,15 @@ static int gn_nhwc_phased(int phases, float* ext_stats, int world, const void* x
     dim3 grid(P.CH, N);
     i2v::gn_stats_nhwc_kernel<<<grid, block, 2 * C * sizeof(float), (cudaStream_t)stream>>>(P);
     CUDA_TRY(cudaGetLastError());
-    const int vg = (N / fg) * G;
-    i2v::gn_finalize_kernel<<<(vg + 7) / 8, 256, 0, (cudaStream_t)stream>>>(P);   // one warp per (video, group)
-    CUDA_TRY(cudaGetLastError());
-    g_launches.fetch_add(2);
+    g_launches.fetch_add(1);
+    // stats + apply in one call: the apply CTAs reduce the partials themselves (tuning key 9 = 1 keeps the separate launch)
+    P.fuse = (phases == 3 && g_tuning[9] == 0) ? 1 : 0;
+    if (!P.fuse) {
+      const int vg = (N / fg) * G;
+      i2v::gn_finalize_kernel<<<(vg + 7) / 8, 256, 0, (cudaStream_t)stream>>>(P);   // one warp per (video, group)
+      CUDA_TRY(cudaGetLastError());
+      g_launches.fetch_add(1);
+    }
   }
   if (!(phases & 2)) return 0;
   // thread = (channel vector, row phase): as many row phases as fit 512 threads

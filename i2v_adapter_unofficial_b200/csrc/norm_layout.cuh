@@ -480,7 +480,8 @@ struct GnNhwcParams {
   float eps;        //   frame partitioner's all-to-all (send buffer written directly, no pack pass)
   int world = 1;    // W of perm = 2
   int raw = 0;      // finalize writes the raw (sum, sum of squares) instead of (mean, rstd): frame-sharded statistics
-};
+  int fuse = 0;     // apply reduces the partials itself (same lane assignment and shuffle tree as gn_finalize_kernel, so the
+};                  //   same bits) instead of reading `stats`: one launch less per GroupNorm
 
 // output row of (video v, position rr, local frame f) in the three layouts of the NHWC GroupNorm family
 __device__ __forceinline__ long long gn_out_row(int perm, int n, int v, int f, int rr, int S, int fg, int V, int world) {
@@ -592,11 +593,33 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnNhwcParams P) 
 // Thread = (channel vector, row phase): the thread's eight channels keep their (A, B, T) coefficients in registers
 // (y = (x + T) * A + B), so the row loop is loads, eight FMAs and a store per 16-byte vector; block = C/8 * rows-per-pass.
 __global__ void __launch_bounds__(512, 2) gn_apply_rows_kernel(const GnNhwcParams P) {
+  __shared__ float2 sm_stats[256];   // fuse: (mean, rstd) of this video's groups
   const int chunk = blockIdx.x, n = blockIdx.y;
   const int v = n / P.fg, f = n - v * P.fg;
   const int VC = P.C / 8;
   const int rpp = blockDim.x / VC;
   const int tcol = threadIdx.x % VC, trow = threadIdx.x / VC;
+  if (P.fuse) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int n_part = P.fg * P.CH;
+    for (int g = warp; g < P.G; g += nwarps) {
+      const float2* base = reinterpret_cast<const float2*>(P.partial) + ((long long)v * P.fg * P.CH) * P.G + g;
+      float a = 0.f, b = 0.f;
+#pragma unroll 4
+      for (int j = lane; j < n_part; j += 32) {
+        const float2 p = base[(long long)j * P.G];
+        a += p.x; b += p.y;
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) {
+        const float cnt = (float)P.fg * (float)(P.C / P.G) * (float)P.S;
+        const float mean = a / cnt;
+        sm_stats[g] = make_float2(mean, rsqrtf(fmaxf(b / cnt - mean * mean, 0.f) + P.eps));
+      }
+    }
+    __syncthreads();
+  }
   if (trow >= rpp) return;
   const int cg = P.C / P.G;
   const bool has_add = P.add != nullptr;
@@ -610,7 +633,8 @@ __global__ void __launch_bounds__(512, 2) gn_apply_rows_kernel(const GnNhwcParam
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int g = (tcol * 8 + k) / cg;
-      const float mean = P.stats[2 * (v * P.G + g)], rstd = P.stats[2 * (v * P.G + g) + 1];
+      const float mean = P.fuse ? sm_stats[g].x : P.stats[2 * (v * P.G + g)];
+      const float rstd = P.fuse ? sm_stats[g].y : P.stats[2 * (v * P.G + g) + 1];
       const float wk = (k & 1) ? bf16_hi(w4[k >> 1]) : bf16_lo(w4[k >> 1]);
       const float bk = (k & 1) ? bf16_hi(b4[k >> 1]) : bf16_lo(b4[k >> 1]);
       A[k] = rstd * wk;

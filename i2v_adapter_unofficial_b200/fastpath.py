@@ -27,6 +27,7 @@ otherwise calls the module's original forward — the stock PyTorch GPU path of 
 """
 from __future__ import annotations
 
+import os
 import functools
 from typing import Any, Callable, Dict, List, Optional
 
@@ -40,6 +41,9 @@ from .processors import _CACHE_EPOCH
 
 #: how often each swapped forward handed the call back to the module's original (stock PyTorch) forward because a
 #: precondition failed -- `bench.py` asserts this stays empty for the measured configuration
+# Transformer2DModel tail (proj_out -> + residual, src/modules/i2v_adapter.py:298-314) on the library's token GEMM with the
+# residual in its epilogue; False keeps cuBLAS + a separate elementwise add (developer A / B switch)
+FUSE_PROJ_OUT_RESIDUAL = os.environ.get("I2V_FUSE_PROJ_OUT", "1") != "0"
 FALLBACKS: Dict[str, int] = {}
 
 
@@ -327,11 +331,20 @@ def _make_transformer2d_forward(module: nn.Module, original: Callable):
                            timestep=bound.get("timestep"), cross_attention_kwargs=bound.get("cross_attention_kwargs"),
                            class_labels=bound.get("class_labels"))
         # :298-314  proj_out -> (BF, C, h, w) -> + residual
-        tokens = F.linear(tokens, module.proj_out.weight.reshape(C, inner), module.proj_out.bias)
-        if nhwc:
-            tokens += hidden_states.permute(0, 2, 3, 1).reshape(N, h * w, C)
+        w_po = module.proj_out.weight.reshape(C, inner)
+        if nhwc and FUSE_PROJ_OUT_RESIDUAL and ops.linear_supported(tokens, w_po):
+            # proj_out + bias + residual in one launch of the library's token GEMM (the residual tile rides in through TMA and
+            # is added after the product is rounded to bf16, as the reference's separate add): one full read-read-write
+            # pass less than `linear` followed by `+=`
+            tokens = ops.linear(tokens, w_po, module.proj_out.bias,
+                                residual=hidden_states.permute(0, 2, 3, 1).reshape(N, h * w, C))
             output = tokens.view(N, h, w, C).permute(0, 3, 1, 2)   # a channels-last (N, C, h, w) tensor, no copy
+        elif nhwc:
+            tokens = F.linear(tokens, w_po, module.proj_out.bias)
+            tokens += hidden_states.permute(0, 2, 3, 1).reshape(N, h * w, C)
+            output = tokens.view(N, h, w, C).permute(0, 3, 1, 2)
         else:
+            tokens = F.linear(tokens, w_po, module.proj_out.bias)
             output = ops.tokens_to_nchw_residual(tokens.contiguous(), hidden_states, 1)
         if not bound.get("return_dict", True):
             return (output,)

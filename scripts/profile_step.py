@@ -22,7 +22,7 @@ def main():
     sched = DDIMScheduler()
     sched.set_timesteps(25)
     ts = [int(t) for t in sched.timesteps]
-    d_in = bench.make_inputs(1, bench.FRAMES, bench.LATENT, 1, torch.bfloat16, device=dev)
+    d_in = bench.make_inputs(1, 16, 64, 1, torch.bfloat16, device=dev)
     lat = d_in["latents"].clone()
     for i in range(3):
         lat = denoise_step(unet, sched, lat, ts[i], d_in["prompt"], 7.5, d_in["cond"], d_in["image"])
