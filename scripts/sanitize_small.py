@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.getcwd())
-from i2v_adapter_unofficial_b200 import ops  # noqa: E402
+from i2v_adapter_unofficial_b200 import _lib, ops  # noqa: E402
 
 torch.manual_seed(0)
 dev = "cuda"
@@ -42,7 +42,13 @@ for dd in (40, 160):
 # IP-Adapter streaming kernel
 q, kv = bf(4, 256, 8, 40), bf(2, 81, 2, 8, 40)
 want = sdpa(q, kv[:, :77, 0], kv[:, :77, 1], 2) + 0.5 * sdpa(q, kv[:, 77:, 0], kv[:, 77:, 1], 2)
+check("ip tcgen05", ops.ip_xattn(q, kv[:, :, 0], kv[:, :, 1], 77, 0.5, 2, None, ops.MODE_FAST), want)
+q = bf(4, 200, 8, 40)   # ragged last query tile: clamped cp.async source rows, guarded stores
+want = sdpa(q, kv[:, :77, 0], kv[:, :77, 1], 2) + 0.5 * sdpa(q, kv[:, 77:, 0], kv[:, 77:, 1], 2)
+check("ip tcgen05 ragged", ops.ip_xattn(q, kv[:, :, 0], kv[:, :, 1], 77, 0.5, 2, None, ops.MODE_FAST), want)
+_lib.load().i2v_set_tuning(5, 4)
 check("ip stream", ops.ip_xattn(q, kv[:, :, 0], kv[:, :, 1], 77, 0.5, 2, None, ops.MODE_FAST), want)
+_lib.load().i2v_set_tuning(5, 0)
 # generic fp32-math kernel
 q, k, v = bf(2, 70, 2, 24), bf(2, 70, 2, 24), bf(2, 70, 2, 24)
 check("generic", ops.sdpa(q, k, v, 1, None, ops.MODE_GENERIC), sdpa(q, k, v))
