@@ -579,7 +579,6 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   P.batch = batch; P.heads = heads; P.sq = seq; P.skv = seq; P.d = d;
   P.scale_log2e = 1.f;
   P.seg_split = -1;
-  P.stagger_clk = g_tuning[8] * 16;   // tuning key 8: start-up skew between the query tiles of a CTA, in units of 16 clk
 #ifdef I2V_TRACE
   P.trace = g_trace;
   P.trace_cta = g_trace_cta;
@@ -605,18 +604,6 @@ int i2v_fused_self_xframe_aug_fwd(const i2v_tensor* q_self, const i2v_tensor* k_
   if (g_tuning[7] == 2) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true, true>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 3) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true, true>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 4) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 0, 3, true, true>>(P, (cudaStream_t)stream);
-  // 16 / 17 / 18 = softmax-warp schedule variants (PipeCfg::SCHED 1 / 2 / 3): early barrier probes + S(j+1) prefetch, centered
-  // reference without the clamp, both; 19 / 20 / 21 = centered with 4 of 8 pairs emulated (degree 3 / 2) and 5 of 8 (degree 2)
-  if (g_tuning[7] == 16) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 0, 1, 1>>(P, (cudaStream_t)stream);
-  if (g_tuning[7] == 17) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 0, 1, 2>>(P, (cudaStream_t)stream);
-  if (g_tuning[7] == 18) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 0, 1, 3>>(P, (cudaStream_t)stream);
-  if (g_tuning[7] == 22) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 0, 1, 4>>(P, (cudaStream_t)stream);   // probes only
-  if (g_tuning[7] == 23) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 0, 1, 5>>(P, (cudaStream_t)stream);   // probes + prefetch
-  if (g_tuning[7] == 24) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 2, 5, 3, 3, true>>(P, (cudaStream_t)stream);   // two query tiles per CTA
-  if (g_tuning[7] == 25) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 1, 5, 3, 3, true>>(P, (cudaStream_t)stream);   // one
-  if (g_tuning[7] == 19) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 3, true, false, 0, 1, 2>>(P, (cudaStream_t)stream);
-  if (g_tuning[7] == 20) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 4, 2, true, false, 0, 1, 2>>(P, (cudaStream_t)stream);
-  if (g_tuning[7] == 21) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 5, 2, true, false, 0, 1, 2>>(P, (cudaStream_t)stream);
 #ifdef I2V_EXPERIMENTS
   if (g_tuning[7] == 7) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 3, 3, true, false, 1>>(P, (cudaStream_t)stream);
   if (g_tuning[7] == 8) return launch_dense_pipe_cfg<i2v::PipeCfg<48, 64, 3, 5, 2, 3, true, false, 1>>(P, (cudaStream_t)stream);

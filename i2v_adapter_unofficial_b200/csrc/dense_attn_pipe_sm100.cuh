@@ -42,18 +42,11 @@ namespace i2v {
 #define I2V_PARK_NS 1000
 #endif
 constexpr uint32_t kParkNs = I2V_PARK_NS;   // suspend-time hint of the producer-side waits
-constexpr float kCenterBias = 59.f;    // SCHED bit 1: the scores arrive as y = s - (m - 59); P = 2^y (the common factor 2^59 cancels in O / l)
-constexpr float kCenterLimit = 67.f;   // fast path while every |y| <= 67, i.e. s - m in [-126, 8]
 constexpr int kAugCol = 40;   // augmented layout: head-dim column that carries -max (Q), ones (K, V) and the row sum (O)
 
 template <int DK_, int BLOCK_N_, int NT_, int NSTAGES_, int EMU_, int DEG_ = 3, bool AUG_ = false, bool SPLIT_ = false,
-          int PAT_ = 0, int MINB_ = 1, int SCHED_ = 0>
+          int PAT_ = 0, int MINB_ = 1>
 struct PipeCfg {
-  // SCHED bit 0: the softmax warp hides its own hand-off latencies -- the barrier states of PV(j-1) / S(j+1) are probed
-  //              while the exponentials still run, and tcgen05.ld of S(j+1) is issued next to tcgen05.st of P(j);
-  //       bit 1: (augmented layout) centered reference -- the max column holds -(m - kCenterBias), so one |x| <= kCenterLimit
-  //              test covers "the row outgrew its reference" and "too small for the FMA-pipe exp2", which drops the clamp.
-  static constexpr int SCHED = SCHED_;
   static constexpr int PAT = PAT_;          // which pairs of every 8 take the FMA-pipe exp2 (softmax_exp_row)
   static constexpr int MINB = MINB_;        // co-resident CTAs per SM (experiment: one query tile per CTA, 3-4 CTAs per SM)
   static constexpr int DK = DK_;            // head dim rounded up to a multiple of 16
@@ -468,11 +461,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
       float l = 0.f;
       bool col_stale = false;   // augmented: m_ref moved, the max column of the query tile must be rewritten
 
-      constexpr bool kPrefetch = (Cfg::SCHED & 1) != 0;
-      constexpr bool kProbe = (Cfg::SCHED & 4) != 0;
-      constexpr bool kCentered = Cfg::AUG && (Cfg::SCHED & 2) != 0;
-      float sv[BN];   // S(j); with kPrefetch the tcgen05.ld of S(j+1) is issued at the end of step j
-      auto issue_load = [&]() {   // (no wait: tc_wait_ld() before the first use)
+      auto load_scores = [&](float (&sv)[BN]) {
         constexpr int N32 = BN / 32, R16 = (BN % 32) / 16;
 #pragma unroll
         for (int cch = 0; cch < N32; ++cch) {
@@ -487,8 +476,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
 #pragma unroll
           for (int i = 0; i < 16; ++i) sv[N32 * 32 + i] = __uint_as_float(r[i]);
         }
+        tc_wait_ld();
       };
-      auto row_max = [&]() -> float {
+      auto row_max = [&](const float (&sv)[BN]) -> float {
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < BN; i += 8) {
@@ -496,17 +486,6 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
           mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
           mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]);
           mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
-        }
-        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      };
-      auto row_abs_max = [&]() -> float {   // (the |.| fold into the FMNMX3 operand modifiers)
-        float mx0 = 0.f, mx1 = 0.f, mx2 = 0.f, mx3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < BN; i += 8) {
-          mx0 = fmax3(mx0, fabsf(sv[i + 0]), fabsf(sv[i + 1]));
-          mx1 = fmax3(mx1, fabsf(sv[i + 2]), fabsf(sv[i + 3]));
-          mx2 = fmax3(mx2, fabsf(sv[i + 4]), fabsf(sv[i + 5]));
-          mx3 = fmax3(mx3, fabsf(sv[i + 6]), fabsf(sv[i + 7]));
         }
         return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       };
@@ -524,7 +503,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
           tmem_st_x16(tm_o + cch * 16, r);
         }
       };
-      auto issue_store_p = [&](const uint32_t (&pk)[BN / 2]) {   // (no wait: tc_wait_st() before the p_full arrival)
+      auto store_p = [&](int j, const uint32_t (&pk)[BN / 2]) {
+        if (j > 0) {   // (j == 0: the epilogue of the previous item already waited for its last PV)
+          mbar_wait(bar_pv_done + t, (it0 + j - 1) & 1);   // PV(j-1) has finished reading the P columns
+          tc_fence_after();
+        }
+        I2V_TRACE_EV(0x6)
         constexpr int H = BN / 2, N16 = H / 16, R8 = (H % 16) / 8;
 #pragma unroll
         for (int cch = 0; cch < N16; ++cch) {
@@ -539,24 +523,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
           for (int i = 0; i < 8; ++i) r[i] = pk[N16 * 16 + i];
           tmem_st_x8(tm_p + N16 * 16, r);
         }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p_full + t);
       };
 
       for (int j = 0; j < n_kv; ++j) {
-        if (!kPrefetch || j == 0) {
-          I2V_TRACE_EV(0x1)
-          mbar_wait(bar_s_full + t, (it0 + j) & 1);
-          if (j == 0 && t > 0 && P.stagger_clk > 0) {
-            // De-phase the tiles of a CTA: their hand-off chains are independent, so a start-up skew persists, and
-            // the sub-partition's XU / FMA pipes see one warp in its hand-off while the others run exponentials
-            // instead of all three warps doing the same thing at the same time.
-            const long long until = clock64() + (long long)t * P.stagger_clk;
-            while (clock64() < until) {}
-          }
-          tc_fence_after();
-          I2V_TRACE_EV(0x2)
-          issue_load();
-        }
-        tc_wait_ld();
+        I2V_TRACE_EV(0x1)
+        mbar_wait(bar_s_full + t, (it0 + j) & 1);
+        tc_fence_after();
+        I2V_TRACE_EV(0x2)
+        float sv[BN];
+        load_scores(sv);
         I2V_TRACE_EV(0x3)
         float m_col_next = m_col;
         if (Cfg::AUG && col_stale) {
@@ -578,10 +556,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
             if (i >= valid) sv[i] = -INFINITY;
         }
         uint32_t pk[BN / 2];
-        bool pv_ok = false, s_ok = false;   // kPrefetch: early probes of PV(j-1) retired / S(j+1) written
         I2V_TRACE_EV(0x4)
         if (!Cfg::AUG) {
-          const float mx = row_max() * c;
+          const float mx = row_max(sv) * c;
           // lazy rescale: the reference max only moves when a row outgrows it by more than 2^kRescaleThreshold
           const bool need = mx > m_ref + kRescaleThreshold;   // m_ref = -inf on the first tile
           if (__any_sync(0xffffffffu, need)) {
@@ -598,29 +575,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
           else      l += softmax_exp_row<BN, 0, 3, true>(sv, c, m_ref, pk);   // -inf padding must go through MUFU
         } else {
           // sv = s - m_col.  Fast path (nothing moved): P = 2^sv straight away; the row sum comes out of the PV MMA
-          // through the ones column of V.  Centered: m_ref / m_col are the reference max minus kCenterBias, and the
-          // fast path needs every |sv| <= kCenterLimit (not too far above the reference, not too small for the
-          // unclamped FMA-pipe exp2); plain: only the row max is tested and the FMA-pipe exp2 clamps.
-          float mx = 0.f;
-          bool need = false, slow;
-          if (kCentered) {
-            slow = (j == 0) || !(row_abs_max() <= kCenterLimit) || (m_col != m_ref) || !full;
-          } else {
-            mx = row_max() + (m_col - m_ref);   // relative to m_ref
-            need = (j == 0) || mx > kRescaleThreshold;
-            slow = need || (m_col != m_ref) || !full;
-          }
+          // through the ones column of V.
+          const float mx = row_max(sv) + (m_col - m_ref);   // relative to m_ref
+          const bool need = (j == 0) || mx > kRescaleThreshold;
+          const bool slow = need || (m_col != m_ref) || !full;
           if (__any_sync(0xffffffffu, slow)) {
-            if (kCentered) {
-              mx = row_max() + (m_col - m_ref);
-              need = (j == 0) || mx > kCenterLimit;
-            }
             if (__any_sync(0xffffffffu, need)) {
               float alpha = 1.f;
               if (need) {
-                // new reference: an integer >= the row max (centered: minus the bias) that bf16 holds exactly (round
-                // the magnitude up / down)
-                const float m_int = ceilf(m_ref + mx) - (kCentered ? kCenterBias : 0.f);
+                // new reference: an integer >= the row max that bf16 holds exactly (round the magnitude up / down)
+                const float m_int = ceilf(m_ref + mx);
                 const uint32_t mb = __float_as_uint(m_int);
                 const float m_new = __uint_as_float(m_int >= 0.f ? ((mb + 0xFFFFu) & 0xFFFF0000u) : (mb & 0xFFFF0000u));
                 alpha = (j == 0) ? 0.f : ex2_approx(m_ref - m_new);
@@ -633,34 +597,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
 #pragma unroll
             for (int i = 0; i < BN; ++i) sv[i] -= delta;
             softmax_exp_row<BN, 0, 3, true, true, false>(sv, 1.f, 0.f, pk);
-          } else if (kProbe) {
-            softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, !kCentered, true, false, Cfg::PAT, 0, BN / 4>(sv, 1.f, 0.f, pk);
-            if (j > 0) pv_ok = mbar_test_wait(bar_pv_done + t, (it0 + j - 1) & 1);
-            softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, !kCentered, true, false, Cfg::PAT, BN / 4, BN / 2>(sv, 1.f, 0.f, pk);
-            if (kPrefetch && j + 1 < n_kv) s_ok = mbar_test_wait(bar_s_full + t, (it0 + j + 1) & 1);
           } else {
-            softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, !kCentered, true, false, Cfg::PAT>(sv, 1.f, 0.f, pk);
+            softmax_exp_row<BN, Cfg::EMU, Cfg::DEG, true, true, false, Cfg::PAT>(sv, 1.f, 0.f, pk);
           }
         }
         m_col = m_col_next;
         I2V_TRACE_EV(0x5)
-        if (j > 0) {   // (j == 0: the epilogue of the previous item already waited for its last PV)
-          if (!pv_ok) mbar_wait(bar_pv_done + t, (it0 + j - 1) & 1);   // PV(j-1) has finished reading the P columns
-          tc_fence_after();
-        }
-        I2V_TRACE_EV(0x6)
-        issue_store_p(pk);
-        if (kPrefetch && j + 1 < n_kv) {
-          // S(j+1) (QK(j+1) was released by our s_free arrival above) on its way to registers while P(j) drains
-          I2V_TRACE_EV(0x1)
-          if (!s_ok) mbar_wait(bar_s_full + t, (it0 + j + 1) & 1);
-          tc_fence_after();
-          issue_load();
-          I2V_TRACE_EV(0x2)
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_p_full + t);
+        store_p(j, pk);
         I2V_TRACE_EV(0x7)
       }
 

@@ -56,7 +56,6 @@ struct DenseParams {
   float seg_scale;     //      form the second segment whose normalised probabilities are multiplied by seg_scale
   unsigned long long* trace;  // developer timeline trace buffer (only read by -DI2V_TRACE builds), else null
   int trace_cta;
-  int stagger_clk;     // pipelined kernel: the softmax warpgroup of query tile t starts every work item t * stagger_clk late
 };
 
 // EMU_ = how many of every 8 (key, key+1) pairs get their 2^x from the FMA-pipe polynomial instead of MUFU.EX2.

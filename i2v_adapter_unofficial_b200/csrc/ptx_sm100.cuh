@@ -53,21 +53,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Non-blocking probe of a phase (try_wait may suspend the warp for a hardware time slice; test_wait never does):
-// issued early, consumed late, it takes the barrier round trip off the critical path of the asking warp.
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // Bounded wait: a protocol bug turns into a trap (reported as a CUDA error by the C-ABI) instead of
 // hanging the GPU box.  The bound is ~2 s of SM clock, far beyond any legitimate wait in these kernels.
 #ifndef I2V_MBAR_TIMEOUT_CYCLES
@@ -564,15 +549,14 @@ __device__ __forceinline__ uint64_t ex2_emu_pair_x(uint64_t x2) {
 // sum.  EMU of every 8 column pairs take the FMA-pipe path; m must be an integer when EMU > 0.
 // PRESCALED: sv already holds x = s*c - m.  SUM = false: the caller gets the row sum elsewhere (ones column of V).
 // PAT = 1: the EMU pairs of every 8 are spread evenly ((i * EMU) % 8 < EMU) instead of taken first.
-// Only the column pairs [I0, I1) are processed (default: all), so a caller can put other work between two halves.
-template <int BN, int EMU, int DEG, bool CLAMP, bool PRESCALED = false, bool SUM = true, int PAT = 0, int I0 = 0, int I1 = BN / 2>
+template <int BN, int EMU, int DEG, bool CLAMP, bool PRESCALED = false, bool SUM = true, int PAT = 0>
 __device__ __forceinline__ float softmax_exp_row(const float (&sv)[BN], float c, float m, uint32_t (&pk)[BN / 2]) {
   const uint64_t c2 = f2_pack(c, c);
   const uint64_t nm2 = f2_pack(-m, -m);
   const uint64_t k1 = f2_pack(kExpMagic - m, kExpMagic - m);
   uint64_t ls0 = 0ull, ls1 = 0ull;
 #pragma unroll
-  for (int i = I0; i < I1; ++i) {
+  for (int i = 0; i < BN / 2; ++i) {
     const uint64_t s2 = f2_pack(sv[2 * i], sv[2 * i + 1]);
     uint64_t p2;
     if (DEG == 0) {
