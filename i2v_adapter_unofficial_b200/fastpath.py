@@ -426,6 +426,18 @@ def _pair_ok(module: nn.Module, x: torch.Tensor, x2: torch.Tensor, temb) -> bool
             and cs.groups == 1 and cs.in_channels == x.shape[1] + x2.shape[1])
 
 
+def _summed_bias(module: nn.Module, slot: str, a: Optional[torch.Tensor], b: torch.Tensor) -> torch.Tensor:
+    """``a + b`` of two per-channel bias vectors, cached on the module (keyed on both parameters' storage and version)."""
+    if a is None:
+        return b
+    cache = module.__dict__.get(slot)
+    if cache is None:
+        from .processors import _PackedWeights
+
+        cache = module.__dict__[slot] = _PackedWeights()
+    return cache.get([a, b], lambda: a + b)
+
+
 def _resnet_forward_nhwc(module: nn.Module, x: torch.Tensor, temb: torch.Tensor,
                          x2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ResnetBlock2D on channels-last activations; with ``x2`` the input is ``torch.cat([x, x2], 1)`` read in place."""
@@ -436,9 +448,20 @@ def _resnet_forward_nhwc(module: nn.Module, x: torch.Tensor, temb: torch.Tensor,
     # constants that the next bandwidth kernel can carry instead: conv1's joins the time-embedding term of norm2,
     # conv2's the residual add
     h = F.conv2d(h, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
-    t = module.time_emb_proj(F.silu(temb))
+    # SiLU(temb) is the same tensor for every ResnetBlock2D of a forward: computed once and kept on `temb` itself; conv1's
+    # bias joins the projection's own bias (cached sum) instead of a separate broadcast add
+    st = getattr(temb, "_b200_silu", None)
+    if st is None:
+        st = F.silu(temb)
+        try:
+            temb._b200_silu = st
+        except Exception:  # noqa: BLE001  (a tensor subclass that refuses attributes: just recompute next time)
+            pass
+    tp = module.time_emb_proj
+    tb = tp.bias
     if c1.bias is not None:
-        t = t + c1.bias
+        tb = _summed_bias(module, "_b200_temb_bias", tp.bias, c1.bias)
+    t = F.linear(st, tp.weight, tb)
     if not ops.is_channels_last(h):
         h = h.contiguous(memory_format=torch.channels_last)
     h = ops.group_norm_nhwc(h, n2.weight, n2.bias, n2.num_groups, n2.eps, 1, silu=True, add=t)
@@ -456,13 +479,13 @@ def _resnet_forward_nhwc(module: nn.Module, x: torch.Tensor, temb: torch.Tensor,
         sc.addmm_(xb, wmat[:, Ca:].t())
         x = sc.view(N, hh, ww, cs.out_channels).permute(0, 3, 1, 2)
         if cs.bias is not None:
-            bias = cs.bias if bias is None else bias + cs.bias
+            bias = cs.bias if bias is None else _summed_bias(module, "_b200_out_bias", bias, cs.bias)
     elif cs is not None:
         if isinstance(cs, nn.Conv2d) and cs.padding_mode == "zeros" and ops.is_channels_last(h):
             # the shortcut convolution's bias rides in the same residual pass as conv2's
             x = F.conv2d(x, cs.weight, None, cs.stride, cs.padding, cs.dilation, cs.groups)
             if cs.bias is not None:
-                bias = cs.bias if bias is None else bias + cs.bias
+                bias = cs.bias if bias is None else _summed_bias(module, "_b200_out_bias", bias, cs.bias)
         else:
             x = cs(x)
     if ops.is_channels_last(x) and ops.is_channels_last(h):

@@ -25,7 +25,7 @@ class Spy(TorchDispatchMode):
         name = str(func).rsplit(".", 1)[0]
         if name in WATCH:
             numel = max([a.numel() for a in args if isinstance(a, torch.Tensor)] + [0])
-            if numel >= 1 << 16:
+            if numel >= 1 << 10:
                 st = [f for f in traceback.extract_stack() if "i2v_adapter_unofficial_b200" in f.filename or "bench.py" in f.filename]
                 where = " <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in st[-3:][::-1])
                 self.hits[(name, where, numel)] += 1

@@ -93,9 +93,10 @@ def main():
         i_txt, i = ncu_digest(ip_rep, f"IP-Adapter cross-attention kernel, level 0 ({TAG})",
                               "Decoupled text (77) + image (4) cross-attention at the C2 level-0 size (32 frames x 4096 "
                               "queries x 8 heads x d=40; reads Q and writes O once: 167.8 MB algorithmic bytes per launch), "
-                              "launched by `scripts/perf_ip_one.py`.  Expected before measuring: HBM-bound by design, in "
-                              "practice limited by dependent mma.sync chains and the two-segment softmax at 72 registers per "
-                              "thread (three CTAs per SM); instantiation with compile-time token counts (77 + 4).")
+                              "launched by `scripts/perf_ip_one.py`: `ip_xattn_tc_kernel` (tcgen05, K / V of one (video, head) resident, "
+                              "three query tiles in flight, Q through cp.async, output through a staging tile).  Expected before "
+                              "measuring: HBM traffic ~ algorithmic (Q read once, O stays in L2), bound by the serial QK -> softmax "
+                              "-> PV -> epilogue chain of a tile, not by a pipe.")
         open(os.path.join(OUT, f"{TAG}_ip_attn_l0.md"), "w").write(i_txt)
         print("ip:", i.get("gpu__time_duration.sum"), "dram r/w", i.get("dram__bytes_read.sum"), i.get("dram__bytes_write.sum"))
     ff_rep = os.path.join(SRC, "prof_ff.ncu-rep")
