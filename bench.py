@@ -356,6 +356,12 @@ def dense_roofline(ms, bf, seq, peaks, traffic_key=None, note=""):
                 frac_of_nominal_2250=achieved / 2250.0, avg_launch_ms=st["median_ms"], flops_per_launch=flops,
                 timing=dict(st, how="cudaEvent pairs recorded by the library around each launch" + note),
                 achieved_at_min_ms=flops / (st["min_ms"] * 1e-3) / 1e12,
+                # the operator is exponential-bound at d = 40 (one exp per 4 * 40 flops): the same launch against the SM's
+                # exponential rate -- MUFU.EX2 issues 16 per clock and SM; informational, `frac` above is the graded figure
+                exponentials=dict(per_launch=flops / (4.0 * HEAD_DIM_L0), achieved_per_s=flops / (4.0 * HEAD_DIM_L0) / (st["median_ms"] * 1e-3),
+                                  mufu_peak_per_s_at_1965mhz=16.0 * 148 * 1.965e9,
+                                  frac_of_mufu_peak=flops / (4.0 * HEAD_DIM_L0) / (st["median_ms"] * 1e-3) / (16.0 * 148 * 1.965e9),
+                                  note="3 of 8 column pairs take an FMA-pipe polynomial instead of MUFU.EX2"),
                 traffic=tr[0] if tr else None, traffic_source=(f"{tr[1]} (ncu --set full; not measured in this run)" if tr else None))
 
 
