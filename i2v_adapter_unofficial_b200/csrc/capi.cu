@@ -257,7 +257,11 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
   // two-segment (IP-Adapter) launches keep all keys in one 128-key tile; at d = 160 that takes the single-query-tile config
   // variant 4 (default): software-pipelined persistent kernel (dense_attn_pipe_sm100.cuh), 3 query tiles x 64 keys
   const bool pipe = dk == 48 && seg_split < 0 && variant >= 3;
-  const int bn = seg_split >= 0 ? 128 : ((dk == 48 && variant >= 1) ? 64 : dense_block_n(dk));
+  // d = 80 (SD1.5 level 1) runs on the pipelined kernel too (two swizzle sub-tiles per row): two query tiles x 64 keys by
+  // default (240 us against 301 us at C2 level 1), tuning key 3 = 6 -> three query tiles x 48 keys (249 us: the ragged third
+  // tile at S = 1024 costs more than the extra tile in flight gains), 3 = 1 -> the first tcgen05 kernel (128 x 128 tiles)
+  const int pipe80 = (dk == 80 && seg_split < 0) ? (g_tuning[3] == 6 ? 48 : g_tuning[3] == 1 ? 0 : 64) : 0;
+  const int bn = seg_split >= 0 ? 128 : pipe80 ? pipe80 : ((dk == 48 && variant >= 1) ? 64 : dense_block_n(dk));
   if (seg_split >= 0 && skv > bn)
     return fail(I2V_ERR_UNSUPPORTED, "two-segment softmax needs skv (%d) <= %d", skv, bn);
   i2v::DenseParams P;
@@ -323,6 +327,22 @@ int launch_dense(const DenseSeg* segs, int nseg, int batch, int heads, int sq, i
       }
     case 64:  return launch_dense_cfg<i2v::DenseCfg<64, 128, 4, 2>>(P, stream);
     case 80:
+      if (pipe80 == 48) {
+        switch (emu) {
+          case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<80, 48, 3, 5, 0>>(P, stream);
+          case 3:  return launch_dense_pipe_cfg<i2v::PipeCfg<80, 48, 3, 5, 3>>(P, stream);
+          default: return launch_dense_pipe_cfg<i2v::PipeCfg<80, 48, 3, 5, 2>>(P, stream);
+        }
+      }
+      if (pipe80 == 64) {
+        switch (emu) {
+          case 0:  return launch_dense_pipe_cfg<i2v::PipeCfg<80, 64, 2, 4, 0>>(P, stream);
+          case 2:  return launch_dense_pipe_cfg<i2v::PipeCfg<80, 64, 2, 4, 2>>(P, stream);
+          case 4:  return launch_dense_pipe_cfg<i2v::PipeCfg<80, 64, 2, 4, 4>>(P, stream);
+          case 5:  return launch_dense_pipe_cfg<i2v::PipeCfg<80, 64, 2, 5, 3>>(P, stream);   // (five-stage ring)
+          default: return launch_dense_pipe_cfg<i2v::PipeCfg<80, 64, 2, 4, 3>>(P, stream);
+        }
+      }
       switch (emu) {
         case 0:  return launch_dense_cfg<i2v::DenseCfg<80, 128, 2, 0>>(P, stream);
         default: return launch_dense_cfg<i2v::DenseCfg<80, 128, 2, 2>>(P, stream);

@@ -66,19 +66,23 @@ struct PipeCfg {
   static constexpr int THREADS = (SM_WARPS + 1 + NT) * 32;  // softmax warpgroups, 1 TMA warp, NT MMA warps
   static_assert(!SPLIT || (AUG && BLOCK_N == 64 && DK == 48), "the column-split softmax exists for the augmented d = 40 layout");
   static constexpr int KSTEPS = DK / 16;
-  static constexpr int Q_TILE_BYTES = 128 * 128;       // one 64-column swizzle sub-tile (DK <= 64)
-  static constexpr int KV_TILE_BYTES = BLOCK_N * 128;
+  static constexpr int KSUB = (DK + 63) / 64;          // 64-column (128-byte) swizzle sub-tiles per row: 1 (d <= 64) or 2 (d = 80)
+  static constexpr int Q_SUB_BYTES = 128 * 128;
+  static constexpr int Q_TILE_BYTES = KSUB * Q_SUB_BYTES;
+  static constexpr int KV_SUB_BYTES = BLOCK_N * 128;
+  static constexpr int KV_TILE_BYTES = KSUB * KV_SUB_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int XCHG_BYTES = SPLIT ? NT * 2 * 128 * 4 : 0;   // SPLIT: per-row maxima the two halves exchange (slow path)
   static constexpr int SMEM_BYTES = NT * Q_TILE_BYTES + NSTAGES * 2 * KV_TILE_BYTES + BAR_BYTES + XCHG_BYTES + 1024;
   static constexpr int TILE_COLS = BLOCK_N + BLOCK_N / 2 + DK;
   static constexpr int TMEM_S = 0, TMEM_P = BLOCK_N, TMEM_O = BLOCK_N + BLOCK_N / 2;  // offsets within a tile's columns
-  static_assert(DK % 16 == 0 && DK <= 64, "pipelined kernel: head dim <= 64");
+  static_assert(DK % 16 == 0 && DK <= 128, "pipelined kernel: head dim <= 128 (two swizzle sub-tiles)");
+  static_assert(!AUG || KSUB == 1, "the augmented layout is the d = 40 -> 48 case");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 128, "BLOCK_N");
   static constexpr int TMEM_COLS = NT * TILE_COLS <= 128 ? 128 : NT * TILE_COLS <= 256 ? 256 : 512;   // allocation: power of two
   static_assert(NT * TILE_COLS <= 512 && MINB * TMEM_COLS <= 512, "TMEM budget");
   static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "smem budget");
-  static_assert(KV_TILE_BYTES % 1024 == 0, "K/V tiles must keep the 1024-byte swizzle-atom alignment");
+  static_assert(KV_SUB_BYTES % 1024 == 0, "K/V tiles must keep the 1024-byte swizzle-atom alignment");
   static_assert(THREADS <= 1024, "CTA size");
 };
 
@@ -167,15 +171,23 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
         if (n > 0) mbar_wait_parked(bar_q_empty, (n - 1) & 1, kParkNs);   // the previous item's QK MMAs are done with sm_q
         mbar_arrive_expect_tx(bar_q_full, it.ntiles * Cfg::Q_TILE_BYTES);
         for (int t = 0; t < it.ntiles; ++t)
-          tma_load_4d(sm_q + t * Cfg::Q_TILE_BYTES, &it.prob->tm_q, bar_q_full, 0, it.h, it.q0 + t * 128, it.b,
-                      kEvictFirst);
+#pragma unroll
+          for (int sub = 0; sub < Cfg::KSUB; ++sub)
+            tma_load_4d(sm_q + t * Cfg::Q_TILE_BYTES + sub * Cfg::Q_SUB_BYTES, &it.prob->tm_q, bar_q_full, sub * 64, it.h,
+                        it.q0 + t * 128, it.b, kEvictFirst);
         for (int j = 0; j < n_kv; ++j, ++g) {
           const int s = g % NS;
           mbar_wait_parked(bar_kv_empty + s, ((g / NS) & 1) ^ 1, kParkNs);
           mbar_arrive_expect_tx(bar_k_full + s, Cfg::KV_TILE_BYTES);
-          tma_load_4d(sm_k + s * Cfg::KV_TILE_BYTES, &it.prob->tm_k, bar_k_full + s, 0, it.h, j * BN, it.bkv, kEvictLast);
+#pragma unroll
+          for (int sub = 0; sub < Cfg::KSUB; ++sub)
+            tma_load_4d(sm_k + s * Cfg::KV_TILE_BYTES + sub * Cfg::KV_SUB_BYTES, &it.prob->tm_k, bar_k_full + s, sub * 64, it.h,
+                        j * BN, it.bkv, kEvictLast);
           mbar_arrive_expect_tx(bar_v_full + s, Cfg::KV_TILE_BYTES);
-          tma_load_4d(sm_v + s * Cfg::KV_TILE_BYTES, &it.prob->tm_v, bar_v_full + s, 0, it.h, j * BN, it.bkv, kEvictLast);
+#pragma unroll
+          for (int sub = 0; sub < Cfg::KSUB; ++sub)
+            tma_load_4d(sm_v + s * Cfg::KV_TILE_BYTES + sub * Cfg::KV_SUB_BYTES, &it.prob->tm_v, bar_v_full + s, sub * 64, it.h,
+                        j * BN, it.bkv, kEvictLast);
         }
       }
     }
@@ -192,7 +204,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
     const uint32_t k_addr = smem_u32(sm_k);
     const uint32_t v_addr = smem_u32(sm_v);
     const uint64_t desc_k_major = make_smem_desc_sw128(0, 16, 1024);
-    const uint64_t desc_v = make_smem_desc_sw128(0, Cfg::KV_TILE_BYTES, 1024);
+    const uint64_t desc_v = make_smem_desc_sw128(0, Cfg::KV_SUB_BYTES, 1024);   // MN-major: 64-column atoms KV_SUB_BYTES apart
     const uint32_t tm_tile = tmem_base + t * Cfg::TILE_COLS;
 
     auto issue_qk = [&](int s) {
@@ -211,8 +223,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) dense_attn_pipe_kerne
 #endif
 #pragma unroll
       for (int kk = 0; kk < KSTEPS; ++kk) {
-        const uint64_t da = desc_k_major | (uint64_t)((qa + kk * 2) & 0x3FFF);   // 32 bytes per 16-column k-step
-        const uint64_t db = desc_k_major | (uint64_t)((ka + kk * 2) & 0x3FFF);
+        // 32 bytes per 16-column k-step inside a 64-column sub-tile
+        const uint32_t sub = kk >> 2, off = (kk & 3) * 2;
+        const uint64_t da = desc_k_major | (uint64_t)((qa + sub * (Cfg::Q_SUB_BYTES >> 4) + off) & 0x3FFF);
+        const uint64_t db = desc_k_major | (uint64_t)((ka + sub * (Cfg::KV_SUB_BYTES >> 4) + off) & 0x3FFF);
         umma_ss(tm_tile + Cfg::TMEM_S, da, db, idesc_qk, kk > 0 ? 1u : 0u);
       }
     };

@@ -318,3 +318,34 @@ def test_ip_adapter_tcgen05_kernel(case):
     finally:
         lib.i2v_set_tuning(5, 0)
     assert (o.float() - o2.float()).abs().max().item() <= BF16_TOL * scale
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# level 1 (d = 80) on the pipelined kernel
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(32, 1024, 16), (8, 2304, 4), (4, 1000, 2), (2, 130, 1)],
+                         ids=["c2_level1", "c4_level1", "ragged", "tiny"])
+def test_fused_self_xframe_d80_pipelined_kernel(case):
+    """`i2v_fused_self_xframe_fwd` at d = 80: the pipelined kernel with two swizzle sub-tiles per row (the default since
+    round 2) at the configs[1] / configs[3] level-1 sizes and on ragged query / key tiles, against torch SDPA in fp32 and
+    against the first tcgen05 kernel (tuning key 3 = 1) on the same operands."""
+    BF, S, Fr = case
+    H, d = 8, 80
+    gen = torch.Generator(device=DEV).manual_seed(BF * S)
+    mk = lambda b: torch.randn(b, S, H, d, device=DEV, generator=gen).to(torch.bfloat16)  # noqa: E731
+    q, k, v, qx, kx, vx = mk(BF), mk(BF), mk(BF), mk(BF), mk(BF // Fr), mk(BF // Fr)
+    o = ops.fused_self_xframe(q, k, v, qx, kx, vx, Fr)
+    t = lambda x: x.transpose(1, 2).float()  # noqa: E731
+    n = min(BF, 4)   # the fp32 reference of a few frames is enough (and all of them for the small cases)
+    ref_s = F.scaled_dot_product_attention(t(q[:n]), t(k[:n]), t(v[:n])).transpose(1, 2)
+    ref_x = F.scaled_dot_product_attention(t(qx[-n:]), t(kx[(BF - n) // Fr:].repeat_interleave(Fr, 0)[-n:]),
+                                           t(vx[(BF - n) // Fr:].repeat_interleave(Fr, 0)[-n:])).transpose(1, 2)
+    assert (o[:n, :, 0].float() - ref_s).abs().max().item() <= BF16_TOL
+    assert (o[-n:, :, 1].float() - ref_x).abs().max().item() <= BF16_TOL
+    lib = _lib.load()
+    lib.i2v_set_tuning(3, 1)
+    try:
+        o_old = ops.fused_self_xframe(q, k, v, qx, kx, vx, Fr)
+    finally:
+        lib.i2v_set_tuning(3, 0)
+    assert (o.float() - o_old.float()).abs().max().item() <= BF16_TOL
