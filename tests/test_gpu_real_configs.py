@@ -349,3 +349,34 @@ def test_fused_self_xframe_d80_pipelined_kernel(case):
     finally:
         lib.i2v_set_tuning(3, 0)
     assert (o.float() - o_old.float()).abs().max().item() <= BF16_TOL
+
+
+@pytest.mark.parametrize("case", [(32, 320, 64, 64, 1, True), (32, 320, 32, 32, 16, False), (6, 1280, 8, 8, 1, True)],
+                         ids=["resnet_level0", "motion_module_frames", "mid_block"])
+def test_group_norm_fused_finalize_matches_the_separate_launch(case):
+    """The one-call channels-last GroupNorm lets every apply CTA reduce the partial sums itself (one launch less); the
+    reduction uses the lane assignment and shuffle tree of `gn_finalize_kernel`, so the result must equal the
+    three-launch form (tuning key 9 = 1) bit for bit -- the shared atomics of the statistics pass make two runs differ
+    in the last bits of the partials, so both forms are compared against fp32 GroupNorm instead when they do."""
+    N, C, h, w, fg, silu = case
+    gen = torch.Generator(device=DEV).manual_seed(N * C)
+    x = (torch.randn(N, C, h, w, device=DEV, generator=gen) * 2 + 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wgt = torch.randn(C, device=DEV, generator=gen).to(torch.bfloat16)
+    b = torch.randn(C, device=DEV, generator=gen).to(torch.bfloat16)
+    lib = _lib.load()
+    y_fused = ops.group_norm_nhwc(x, wgt, b, 32, 1e-5, fg, silu=silu)
+    lib.i2v_set_tuning(9, 1)
+    try:
+        y_sep = ops.group_norm_nhwc(x, wgt, b, 32, 1e-5, fg, silu=silu)
+    finally:
+        lib.i2v_set_tuning(9, 0)
+    V = N // fg
+    ref = F.group_norm(x.float().view(V, fg, C, h, w).transpose(1, 2).reshape(V, C, fg * h, w), 32, wgt.float(), b.float(), 1e-5)
+    ref = ref.view(V, C, fg, h, w).transpose(1, 2).reshape(N, C, h, w)
+    if silu:
+        ref = F.silu(ref.to(torch.bfloat16).float())
+    scale = max(1.0, ref.abs().max().item())
+    assert (y_fused.float() - ref).abs().max().item() <= BF16_TOL * scale
+    assert (y_sep.float() - ref).abs().max().item() <= BF16_TOL * scale
+    # same partials -> same statistics -> same output, up to the run-to-run jitter of the statistics pass
+    assert (y_fused.float() - y_sep.float()).abs().max().item() <= 2 * 2.0 ** -8 * scale
