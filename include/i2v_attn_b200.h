@@ -220,10 +220,13 @@ int i2v_gn_nhwc_apply(const void* x, const void* add, const void* w, const void*
 int i2v_rows_residual_sharded(const void* y, const void* res, void* out, int N, int S, int C, int fg, int world,
                               void* stream);
 
-/* Tuning knobs for experiments (0 = library default).  key 0: temporal stages, key 1: temporal CTAs per SM,
+/* Tuning knobs for experiments (0 = library default; keys 0..11).  key 0: temporal stages, key 1: temporal CTAs per SM,
  * key 2: dense-attention exp2 split + 1 (pairs out of 8 computed on the FMA pipe instead of MUFU),
- * key 3: dense-attention tile variant + 1 for head dims <= 48 (see capi.cu), key 5: 1 = IP-Adapter attention on the
- * tcgen05 single-tile kernel instead of the streaming kernel, key 6: streaming-kernel configuration. */
+ * key 3: dense-attention tile variant + 1 for head dims <= 48; at d = 80: 1 = the first tcgen05 kernel instead of the
+ * pipelined one, 6 = three query tiles x 48 keys (see capi.cu), key 4: temporal rows per warp, key 5: IP-Adapter
+ * attention -- 1 = tcgen05 single-tile dense kernel, 4 = streaming kernel even where the resident-K/V tcgen05 kernel
+ * applies, key 6: token-GEMM tile width / streaming-kernel configuration, key 7: variants of the augmented-layout dense
+ * kernel (profiles/r02_dense_experiments.md), key 9: 1 = channels-last GroupNorm with the separate finalize launch. */
 int i2v_set_tuning(int key, int value);
 
 /* Launch timing for bench.py ("the dominant kernel timed live with CUDA events on the launching
