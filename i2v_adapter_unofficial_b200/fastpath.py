@@ -450,11 +450,13 @@ def _resnet_forward_nhwc(module: nn.Module, x: torch.Tensor, temb: torch.Tensor,
     h = F.conv2d(h, c1.weight, None, c1.stride, c1.padding, c1.dilation, c1.groups)
     # SiLU(temb) is the same tensor for every ResnetBlock2D of a forward: computed once and kept on `temb` itself; conv1's
     # bias joins the projection's own bias (cached sum) instead of a separate broadcast add
-    st = getattr(temb, "_b200_silu", None)
-    if st is None:
+    cached = getattr(temb, "_b200_silu", None)
+    if cached is not None and cached[0] == temb._version:
+        st = cached[1]
+    else:
         st = F.silu(temb)
         try:
-            temb._b200_silu = st
+            temb._b200_silu = (temb._version, st)   # (an in-place write to temb bumps its version: recomputed then)
         except Exception:  # noqa: BLE001  (a tensor subclass that refuses attributes: just recompute next time)
             pass
     tp = module.time_emb_proj
