@@ -380,3 +380,50 @@ def test_group_norm_fused_finalize_matches_the_separate_launch(case):
     assert (y_sep.float() - ref).abs().max().item() <= BF16_TOL * scale
     # same partials -> same statistics -> same output, up to the run-to-run jitter of the statistics pass
     assert (y_fused.float() - y_sep.float()).abs().max().item() <= 2 * 2.0 ** -8 * scale
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# one UNet forward at the benchmark shapes themselves (every kernel at the size bench.py times it at, in the system)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(16, 64), (16, 96)], ids=["configs1_64x64", "configs3_96x96"])
+def test_unet_forward_at_benchmark_shapes_matches_fp32_stock_processors(case):
+    """BASELINE.json configs[1] / configs[3] exactly as bench.py runs them (CFG batch of one video, 16 frames, 64 x 64 /
+    96 x 96 latent, 77 text + 4 image tokens): one UNet forward with the B200 processors + fast path in bf16 against the
+    stock SDPA processors in fp32 on the same GPU and weights.  Level 0 then runs at S = 4096 / 9216 (pipelined d = 40
+    kernel, IP-Adapter tcgen05 kernel with 32 / 72 query tiles per frame), level 1 at S = 1024 / 2304 (pipelined d = 80
+    kernel), the temporal kernel at 8192 / 18432 positions."""
+    frames, size = case
+    torch.manual_seed(0)
+    unet = UNetMotionCrossFrameAttnModel(**SD15).eval()
+    unet._load_ip_adapter_weights(fake_ip_adapter_state_dict(unet, 3, image_embed_dim=64))
+    unet = _nonzero_adapter_out(randomize_zero_init(unet))
+    g = torch.Generator().manual_seed(5)
+    sample = torch.randn(2, frames, 4, size, size, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    img = torch.randn(2, 64, generator=g)
+
+    def run(dtype, b200):
+        model = unet.to(DEV, dtype)
+        handle = install(model) if b200 else None
+        if b200:
+            fastpath.reset_fallback_counts()
+        with torch.no_grad():
+            out = model(sample.to(DEV, dtype), 481, enable_cross_frame_attn=True, encoder_hidden_states=ctx.to(DEV, dtype),
+                        added_cond_kwargs={"image_embeds": img.to(DEV, dtype)}).sample.float().cpu()
+        if b200:
+            assert fastpath.fallback_counts() == {}
+            handle.uninstall()
+        torch.cuda.empty_cache()
+        return out
+
+    ref32 = run(torch.float32, False)
+    stock16 = run(torch.bfloat16, False)
+    ours16 = run(torch.bfloat16, True)
+    cos = lambda a, b: F.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()  # noqa: E731
+    e_ours = (ours16 - ref32).abs().max().item() / ref32.abs().max().item()
+    e_stock = (stock16 - ref32).abs().max().item() / ref32.abs().max().item()
+    print(f"UNet forward {frames} f {size} x {size}: cosine ours-bf16 vs fp32 {cos(ours16, ref32):.6f} (stock bf16 {cos(stock16, ref32):.6f}), "
+          f"max-abs / range ours {e_ours:.4f} stock {e_stock:.4f}")
+    assert torch.isfinite(ours16).all()
+    assert cos(ours16, ref32) >= 0.999
+    assert e_ours <= max(2e-2, 2.0 * e_stock)   # no worse than twice what bf16 storage alone costs the stock path
