@@ -49,13 +49,6 @@ struct FfGegluParams {
   int m_tiles, n_tiles;
 };
 
-#ifndef I2V_FF_WARP_STORE
-#define I2V_FF_WARP_STORE 1
-#endif
-#ifndef I2V_FF_MUFU
-#define I2V_FF_MUFU 0
-#endif
-constexpr int kFfMufuPairs = I2V_FF_MUFU;          // of every 4 output pairs, how many evaluate the GELU with MUFU.RCP + MUFU.EX2
 constexpr int kFfStages = 3;
 constexpr int kFfEpiWarps = 16;                    // lane quarter x group of 32 output columns
 constexpr int kFfThreads = (kFfEpiWarps + 2) * 32; // epilogue warps, TMA warp, MMA warp
@@ -260,46 +253,6 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
         if (CL == 1) mbar_arrive(bar_acc_empty + b);
         else mbar_arrive_cluster(bar_acc_empty + b, 0u);   // the leader's barrier
       }
-#if I2V_FF_WARP_STORE
-      // Output through a warp-private staging block (32 rows x 64 B, 16-byte chunks XOR-swizzled by the row) and
-      // memory-order stores: every store instruction writes eight complete 64-byte row segments.  No CTA-wide barrier, no
-      // TMA store whose shared-memory read the next tile would have to wait for.
-      uint8_t* wst = sm_out + warp * 2048;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const uint32_t* hc = h[ch];
-        const uint32_t* gc = gt[ch];
-        const uint64_t* bh2 = reinterpret_cast<const uint64_t*>(wb + ch * 16);
-        const uint64_t* bg2 = reinterpret_cast<const uint64_t*>(wb + 32 + ch * 16);
-        uint32_t o[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t h2 = f2_add(f2_pack(__uint_as_float(hc[2 * k]), __uint_as_float(hc[2 * k + 1])), bh2[k]);
-          const uint64_t g2 = f2_add(f2_pack(__uint_as_float(gc[2 * k]), __uint_as_float(gc[2 * k + 1])), bg2[k]);
-          float r0, r1;
-          f2_unpack((k & 3) < kFfMufuPairs ? geglu_pair_mufu(h2, g2) : geglu_pair_poly(h2, g2), r0, r1);
-          o[k] = bf16_pack(r0, r1);
-        }
-        *reinterpret_cast<uint4*>(wst + lane * 64 + (((2 * ch) ^ (lane >> 1)) & 3) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(wst + lane * 64 + (((2 * ch + 1) ^ (lane >> 1)) & 3) * 16) = make_uint4(o[4], o[5], o[6], o[7]);
-      }
-      if (P.ld > P.N && nt == 0 && half == 0 && row < P.rows)   // ones column for the next GEMM's deferred bias
-        *reinterpret_cast<uint4*>(P.out + row * P.ld + P.N) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-      __syncwarp();
-      {
-        const long long row0 = row - lane;   // first row of this warp's block
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int g = k * 32 + lane, r = g >> 2, c = g & 3;
-          const uint4 v = *reinterpret_cast<const uint4*>(wst + r * 64 + ((c ^ (r >> 1)) & 3) * 16);
-          if (row0 + r < P.rows) *reinterpret_cast<uint4*>(P.out + (row0 + r) * P.ld + n0 + c * 8) = v;
-        }
-      }
-      __syncwarp();   // (the block is rewritten by the next tile)
-    }
-  }
-
-#else
       // the staging tile is free once the previous tile's stores have read it (the issuing thread waits, then everyone
       // passes this barrier)
       if (threadIdx.x == 0 && i > 0) tma_store_wait_read();
@@ -316,8 +269,7 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
           const uint64_t h2 = f2_add(f2_pack(__uint_as_float(hc[2 * k]), __uint_as_float(hc[2 * k + 1])), bh2[k]);
           const uint64_t g2 = f2_add(f2_pack(__uint_as_float(gc[2 * k]), __uint_as_float(gc[2 * k + 1])), bg2[k]);
           float r0, r1;
-          // kFfMufuPairs of every 4 pairs take the XU form of the GELU, the others the FMA-pipe polynomial
-          f2_unpack((k & 3) < kFfMufuPairs ? geglu_pair_mufu(h2, g2) : geglu_pair_poly(h2, g2), r0, r1);
+          f2_unpack(geglu_pair_poly(h2, g2), r0, r1);
           o[k] = bf16_pack(r0, r1);
         }
         // 128-byte swizzle: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
@@ -337,7 +289,6 @@ __global__ void __launch_bounds__(kFfThreads, 1) ff_geglu_gemm_kernel(const __gr
     }
   }
 
-#endif
   if (threadIdx.x == 0) tma_store_wait_all();     // the last tile's stores have left shared memory and are complete
   tc_fence_before();
   __syncthreads();

@@ -269,30 +269,6 @@ __device__ __forceinline__ uint64_t geglu_pair_poly(uint64_t h2, uint64_t g2) {
   return f2_mul(h2, f2_sub(relu2, r));
 }
 
-// The same product with the erf of gelu_erf_fast (A&S 7.1.26: one MUFU.RCP and one MUFU.EX2 per value) on packed pairs:
-// 12 packed FMA-pipe instructions + 4 XU ops per pair against 17 packed for the polynomial.  The feed-forward epilogue
-// mixes the two forms so that the FMA and XU pipes of a sub-partition finish together.
-__device__ __forceinline__ uint64_t geglu_pair_mufu(uint64_t h2, uint64_t g2) {
-  float g0, g1;
-  f2_unpack(g2, g0, g1);
-  const uint64_t a2 = f2_pack(fabsf(g0), fabsf(g1));
-  float d0, d1, x0, x1, t0, t1, e0, e1;
-  f2_unpack(f2_fma(a2, f2_pack(0.23164189f, 0.23164189f), f2_pack(1.f, 1.f)), d0, d1);
-  f2_unpack(f2_mul(f2_mul(g2, f2_pack(-0.72134752f, -0.72134752f)), g2), x0, x1);   // -g^2 log2(e) / 2
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
-  const uint64_t t2 = f2_pack(t0, t1);
-  uint64_t q = f2_fma(t2, f2_pack(0.5307027145f, 0.5307027145f), f2_pack(-0.7265760135f, -0.7265760135f));
-  q = f2_fma(q, t2, f2_pack(0.7107068705f, 0.7107068705f));
-  q = f2_fma(q, t2, f2_pack(-0.142248368f, -0.142248368f));
-  q = f2_fma(q, t2, f2_pack(0.127414796f, 0.127414796f));
-  const uint64_t r = f2_mul(f2_mul(a2, f2_pack(e0, e1)), f2_mul(q, t2));   // |g| e^{-g^2/2} q(t) t
-  const uint64_t relu2 = f2_pack(fmaxf(g0, 0.f), fmaxf(g1, 0.f));
-  return f2_mul(h2, f2_sub(relu2, r));
-}
-
 __device__ __forceinline__ uint4 geglu_vec(const uint4 h, const uint4 g) {
   const uint32_t hin[4] = {h.x, h.y, h.z, h.w}, gin[4] = {g.x, g.y, g.z, g.w};
   uint32_t out[4];
